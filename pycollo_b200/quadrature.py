@@ -1,0 +1,211 @@
+"""Collocation point sets, quadrature weights and integration blocks.
+
+Host-side, once-per-settings tables that end up as device-resident constants
+of the CUDA engine.  Written from the mathematical
+definitions, not from the reference's generator:
+
+* Lobatto (LGL) points are the roots of ``P'_{n-1}`` plus the two ends, found by
+  Newton iteration on the Legendre recurrence; weights ``1/(n(n-1)P_{n-1}(x)^2)``
+  (the reference normalises Lobatto weights to sum to ONE, see
+  ``pycollo/quadrature.py:201-203`` and ``tests/unit/test_quadrature.py:48-55``).
+* Radau (LGR, left end included) points are the ``n-1`` roots of
+  ``P_{n-2}+P_{n-1}`` and a padding entry; weights sum to TWO and the padding
+  weight is exactly 0 (``pycollo/quadrature.py:116-139``).  This asymmetry
+  (sum 1 vs sum 2) is the reference's behaviour and is kept on purpose
+  ("Radau quirk").
+* The integration block ``A`` (``(n-1) x n``) is the collocation matrix
+  ``A[l, j] = integral_0^{c_{l+1}} L_j(t) dt`` on the unit interval, which is the
+  unique solution of the simplifying conditions the reference solves
+  numerically (``pycollo/quadrature.py:141-163, 214-246``).  Its last row is
+  the weight vector on [0, 1].  Under Radau the last column is exactly zero.
+
+Agreement with the reference's own tables is pinned by
+``tests/test_quadrature_mesh.py`` against ``tests/golden/quadrature_*.npz``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+LOBATTO = "lobatto"
+RADAU = "radau"
+GAUSS = "gauss"
+QUADRATURE_METHODS = (LOBATTO, RADAU)
+DEFAULT_COLLOCATION_POINTS_MIN = 4
+DEFAULT_COLLOCATION_POINTS_MAX = 10
+
+
+def _legendre_pair(n, x):
+    """Return (P_n(x), P_{n-1}(x)) by the three-term recurrence (vectorised)."""
+    x = np.asarray(x, dtype=np.float64)
+    p_prev = np.ones_like(x)
+    if n == 0:
+        return p_prev, np.zeros_like(x)
+    p = x.copy()
+    for k in range(1, n):
+        p, p_prev = ((2 * k + 1) * x * p - k * p_prev) / (k + 1), p
+    return p, p_prev
+
+
+def _legendre_derivs(n, x):
+    """P_n, P_n', P_n'' at interior points x (|x| < 1)."""
+    p, pm1 = _legendre_pair(n, x)
+    one_m_x2 = 1.0 - x * x
+    dp = n * (pm1 - x * p) / one_m_x2
+    ddp = (2.0 * x * dp - n * (n + 1) * p) / one_m_x2
+    return p, dp, ddp
+
+
+def _lobatto_points(n):
+    if n == 2:
+        return np.array([-1.0, 1.0])
+    m = n - 1
+    k = np.arange(1, m)
+    x = -np.cos(np.pi * k / m)  # Chebyshev-Lobatto start
+    for _ in range(100):
+        _, dp, ddp = _legendre_derivs(m, x)
+        step = dp / ddp
+        x = x - step
+        if np.max(np.abs(step)) < 1e-16:
+            break
+    x = 0.5 * (x - x[::-1])  # enforce exact antisymmetry
+    return np.concatenate([[-1.0], x, [1.0]])
+
+
+def _radau_points(n):
+    """The n-1 left-Radau points (roots of P_{n-2} + P_{n-1}), ascending."""
+    m = n - 1  # number of true points
+    if m == 1:
+        return np.array([-1.0])
+    # interior roots of (P_{m-1}+P_m)/(1+x); start from Chebyshev-like guesses
+    k = np.arange(1, m)
+    x = -np.cos(2.0 * np.pi * k / (2 * m - 1))
+    for _ in range(200):
+        pm, pm1 = _legendre_pair(m, x)
+        f = pm + pm1
+        one_m_x2 = 1.0 - x * x
+        dpm = m * (pm1 - x * pm) / one_m_x2
+        if m - 1 == 0:
+            dpm1 = np.zeros_like(x)
+        else:
+            pm1_, pm2 = _legendre_pair(m - 1, x)
+            dpm1 = (m - 1) * (pm2 - x * pm1_) / one_m_x2
+        df = dpm + dpm1
+        # deflate the known root at -1: g = f/(1+x)
+        g = f / (1.0 + x)
+        dg = (df - g) / (1.0 + x)
+        step = g / dg
+        x = x - step
+        if np.max(np.abs(step)) < 1e-16:
+            break
+    return np.concatenate([[-1.0], np.sort(x)])
+
+
+def _collocation_matrix(c):
+    """A[i, j] = int_0^{c_i} L_j(t) dt for distinct abscissae c on [0, 1]."""
+    c = np.asarray(c, dtype=np.float64)
+    s = len(c)
+    # barycentric weights
+    diff = c[:, None] - c[None, :]
+    np.fill_diagonal(diff, 1.0)
+    bw = 1.0 / np.prod(diff, axis=1)
+    ng = s // 2 + 2
+    xg, wg = np.polynomial.legendre.leggauss(ng)
+    A = np.zeros((s, s))
+    for i in range(s):
+        if c[i] == 0.0:
+            continue
+        t = 0.5 * c[i] * (xg + 1.0)
+        w = 0.5 * c[i] * wg
+        # Lagrange basis at quadrature abscissae via the product form
+        L = np.ones((len(t), s))
+        for j in range(s):
+            for k in range(s):
+                if k != j:
+                    L[:, j] *= (t - c[k]) / (c[j] - c[k])
+        A[i, :] = w @ L
+    del bw
+    return A
+
+
+class Quadrature:
+    """Tables for one quadrature scheme; orders are generated lazily.
+
+    Mirrors the query surface of the reference class
+    (``pycollo/quadrature.py:40-114``): ``quadrature_point(order, domain=)``,
+    ``quadrature_weight(order)``, ``butcher_array(order)``, ``A_matrix(order)``
+    (integration block, rows 1.. of the Butcher array) and ``D_matrix(order)``
+    (the ``[1 | -I]`` difference block).
+    """
+
+    def __init__(self, method=LOBATTO):
+        if method == GAUSS:
+            raise ValueError("gauss quadrature is unsupported "
+                             "(pycollo/quadrature.py:34-35)")
+        if method not in QUADRATURE_METHODS:
+            raise ValueError(f"unknown quadrature method {method!r}")
+        self.method = method
+        self._cache = {}
+
+    def _tables(self, order):
+        order = int(order)
+        if order < 2:
+            raise ValueError("a mesh section needs at least two nodes")
+        tab = self._cache.get(order)
+        if tab is None:
+            tab = (self._lobatto(order) if self.method == LOBATTO
+                   else self._radau(order))
+            self._cache[order] = tab
+        return tab
+
+    @staticmethod
+    def _lobatto(n):
+        x = _lobatto_points(n)
+        p, _ = _legendre_pair(n - 1, x)
+        w = 1.0 / (n * (n - 1) * p * p)
+        c = 0.5 * (x + 1.0)
+        butcher = _collocation_matrix(c)
+        butcher[0, :] = 0.0
+        butcher[-1, :] = w
+        return {"points": x, "weights": w, "butcher": butcher}
+
+    @staticmethod
+    def _radau(n):
+        xr = _radau_points(n)
+        m = n - 1
+        pm1, _ = _legendre_pair(m - 1, xr) if m >= 1 else (np.ones_like(xr), None)
+        w_true = np.empty(m)
+        w_true[0] = 2.0 / m ** 2
+        if m > 1:
+            w_true[1:] = (1.0 - xr[1:]) / (m ** 2 * pm1[1:] ** 2)
+        x = np.concatenate([xr, [0.0]])
+        w = np.concatenate([w_true, [0.0]])
+        c = 0.5 * (xr + 1.0)
+        inner = _collocation_matrix(c)          # (n-1) x (n-1), row 0 is zero
+        butcher = np.zeros((n, n))
+        butcher[:m, :m] = inner
+        butcher[0, :] = 0.0
+        butcher[-1, :] = w / 2.0
+        return {"points": x, "weights": w, "butcher": butcher}
+
+    def quadrature_point(self, order, *, domain=None):
+        pts = self._tables(order)["points"]
+        if domain is not None:
+            stretch = 0.5 * (domain[1] - domain[0])
+            shift = 0.5 * (domain[0] + domain[1])
+            return stretch * pts + shift
+        return pts
+
+    def quadrature_weight(self, order):
+        return self._tables(order)["weights"]
+
+    def butcher_array(self, order):
+        return self._tables(order)["butcher"]
+
+    def A_matrix(self, order):
+        """Integration block: (order-1) x order (``pycollo/quadrature.py:170``)."""
+        return self._tables(order)["butcher"][1:, :]
+
+    def D_matrix(self, order):
+        """Difference block ``[1 | -I]`` (``pycollo/quadrature.py:165-168``)."""
+        n = int(order)
+        return np.hstack([np.ones((n - 1, 1)), -np.eye(n - 1)])
