@@ -1,0 +1,161 @@
+/* pcx.h -- C ABI of the pycollo_b200 NLP-callback engine (libpcx.so).
+ *
+ * Drop-in boundary for the per-iterate callbacks of pycollo's direct
+ * collocation NLP.  Nothing like this exists in the reference (it is 100 %
+ * Python over CasADi); each entry point names the reference interface it
+ * replaces.  Paths are relative to the reference tree.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types;
+ *   - every function returns 0 on success, a negative PCX_E* code otherwise;
+ *     pcx_last_error(engine) (or pcx_last_error(NULL) after a failed
+ *     pcx_create) gives the message; no exception crosses this boundary;
+ *   - x is the *scaled* iterate x_tilde (x = V*x_tilde + r), layout
+ *     pycollo/backend.py:1433-1457; c layout backend.py:1551-1563;
+ *   - Jacobian values follow CasADi CCS order (sorted by column, then row):
+ *     pycollo/backend.py:1747-1761; Hessian values are the upper triangle in
+ *     CCS order of sigma*J + lam.c (ca.nlpsol convention, backend.py:1693);
+ *   - `space` says where the caller's buffers live: PCX_HOST (pageable or
+ *     pinned host memory; the call copies in/out and synchronises) or
+ *     PCX_DEVICE (device pointers; the call only enqueues on `stream`);
+ *   - one engine = one CUDA device + one problem + one mesh; an engine is not
+ *     thread-safe, distinct engines are independent;
+ *   - `batch` independent iterates of the same problem are evaluated per call
+ *     (multi-start / parameter sweep): every vector argument is
+ *     batch-major, instance i at offset i * length.
+ *   - there is NO CPU fallback: without a CUDA device every evaluation fails
+ *     with PCX_ECUDA.
+ */
+#ifndef PCX_H
+#define PCX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCX_OK        0
+#define PCX_EINVAL   -1   /* bad argument / missing table                 */
+#define PCX_ECUDA    -2   /* CUDA runtime or driver error                 */
+#define PCX_ENVRTC   -3   /* NVRTC compilation of the kernels failed      */
+#define PCX_ENOMEM   -4
+
+#define PCX_HOST   0
+#define PCX_DEVICE 1
+
+/* evaluation selectors (bit-or) */
+#define PCX_EVAL_C     1   /* constraint vector                            */
+#define PCX_EVAL_DY    2   /* state derivatives at all nodes               */
+#define PCX_EVAL_JAC   4   /* Jacobian non-zeros                           */
+#define PCX_EVAL_HESS  8   /* Lagrangian Hessian non-zeros                 */
+#define PCX_EVAL_F     16  /* objective                                    */
+#define PCX_EVAL_GRAD  32  /* objective gradient (dense)                   */
+
+typedef struct pcx_engine pcx_engine;
+
+/* A named host array uploaded once at creation (sparsity maps, tiling,
+ * quadrature tables ...).  Names and element types: pcx_table_name(i),
+ * pcx_table_elem_size(i). */
+typedef struct {
+    const char* name;
+    const void* data;
+    int64_t     bytes;
+} pcx_table;
+
+typedef struct {
+    int32_t device;          /* CUDA ordinal                                   */
+    int32_t threads;         /* CTA size the tiling was built for              */
+    int32_t batch;           /* instances per call                             */
+    int32_t num_tiles;
+    int32_t nvmax;           /* max (states+controls) over phases              */
+    int32_t n_border;        /* border-map entries                             */
+    int32_t bv_size;         /* border value vector length                     */
+    int32_t nred_max;        /* max reductions per phase                       */
+    int32_t btab_len;        /* quadrature coefficient table length            */
+    int32_t reserved;
+    int64_t num_x, num_c, num_dy, nnz_g, nnz_h;
+    int64_t smem_bytes;      /* dynamic shared memory per CTA                  */
+    const char* problem_header;  /* generated device functions (CUDA C++)     */
+    int32_t num_tables;
+    const pcx_table* tables;
+} pcx_spec;
+
+/* ---- lifetime ------------------------------------------------------------
+ * Replaces Casadi.generate_nlp_function_callables + create_nlp_solver
+ * (pycollo/backend.py:1403-1411, 1681-1693): compiles the callbacks for one
+ * problem (NVRTC, sm_100a) and uploads the mesh-dependent tables.           */
+int  pcx_create(const pcx_spec* spec, pcx_engine** out);
+void pcx_destroy(pcx_engine* e);
+const char* pcx_last_error(const pcx_engine* e);
+const char* pcx_version(void);
+
+/* names / element sizes of the tables pcx_create expects */
+int         pcx_table_count(void);
+const char* pcx_table_name(int i);
+int         pcx_table_elem_size(int i);
+
+/* Replaces the substitution of numeric w, W, V, r into the CasADi graph
+ * (backend.py:1459-1463, 1684-1689; scaling.py:164-170, 346-430): rewrites the
+ * small scaling-dependent tables; no recompilation.                         */
+int pcx_set_scaling(pcx_engine* e,
+                    const double* pscal, int64_t n_pscal,
+                    const double* gscal, int64_t n_gscal,
+                    const double* border_coef, int64_t n_border_coef,
+                    const double* pt_scal, int64_t n_pt_scal);
+
+/* ---- evaluation ------------------------------------------------------------
+ * Generic entry: any combination of PCX_EVAL_* in one fused launch.  Unused
+ * outputs may be NULL.  sigma may be NULL (= 1).                            */
+int pcx_eval(pcx_engine* e, int what,
+             const double* x, const double* lam, const double* sigma,
+             double* f, double* grad, double* c, double* dy,
+             double* jac, double* hess, int space, void* stream);
+
+/* nlp_f      : Casadi.evaluate_J             backend.py:1713-1715            */
+int pcx_eval_f(pcx_engine* e, const double* x, double* f, int space, void* stream);
+/* nlp_grad_f : Casadi.evaluate_g             backend.py:1717-1720            */
+int pcx_eval_grad(pcx_engine* e, const double* x, double* grad, int space, void* stream);
+/* nlp_g      : Casadi.evaluate_c             backend.py:1722-1725            */
+int pcx_eval_c(pcx_engine* e, const double* x, double* c, int space, void* stream);
+/* dy         : Casadi.dy_iter_callable       backend.py:1665-1668,
+ *              solution/casadi_solution.py:71                                */
+int pcx_eval_dy(pcx_engine* e, const double* x, double* dy, int space, void* stream);
+/* nlp_jac_g  : Casadi.evaluate_G_nonzeros    backend.py:1738-1745            */
+int pcx_eval_jac(pcx_engine* e, const double* x, double* jac, int space, void* stream);
+/* nlp_hess_l : exact Hessian inside ca.nlpsol, backend.py:1693 (the
+ *              reference's evaluate_H* raise NotImplementedError, :1773-1805) */
+int pcx_eval_hess(pcx_engine* e, const double* x, const double* lam,
+                  const double* sigma, double* hess, int space, void* stream);
+/* BASELINE metric: one "eval" = Jacobian + Hessian values, one launch.       */
+int pcx_eval_jac_hess(pcx_engine* e, const double* x, const double* lam,
+                      const double* sigma, double* jac, double* hess,
+                      int space, void* stream);
+
+/* Sizes (per instance) -- Casadi.evaluate_G_num_nonzero backend.py:1763-1771 */
+int pcx_sizes(const pcx_engine* e, int64_t* num_x, int64_t* num_c, int64_t* num_dy,
+              int64_t* nnz_jac, int64_t* nnz_hess, int32_t* batch);
+
+/* Permuted views for a cyipopt-style host (row-major Jacobian, lower-triangular
+ * Hessian; pycollo/nlp.py:36-76, iteration.py:930-933, 965-968):
+ * out[i] = in[perm[i]] on the device.                                        */
+int pcx_gather(pcx_engine* e, const double* in, const int64_t* perm, int64_t n,
+               double* out, int space, void* stream);
+
+/* Pinned host buffers for the caller (async H2D/D2H of iterates and values). */
+int pcx_host_alloc(void** ptr, int64_t bytes);
+int pcx_host_free(void* ptr);
+
+/* Number of kernel launches issued by this engine since creation, and the
+ * names of the compiled kernel variants (diagnostics for bench.py).          */
+int64_t pcx_launch_count(const pcx_engine* e);
+int     pcx_synchronize(pcx_engine* e, void* stream);
+
+/* Write `bytes` bytes of scratch on the device (> L2) so the next timed launch
+ * starts from a cold L2.                                                     */
+int pcx_flush_l2(pcx_engine* e, int64_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCX_H */

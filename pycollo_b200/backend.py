@@ -1,0 +1,511 @@
+"""``backend="cuda"``: the drop-in for pycollo's CasADi evaluation path.
+
+Mirrors, for the per-iterate callback path only, the surface the rest of pycollo
+calls on its backend:
+
+* ``Cuda`` stands where ``pycollo.backend.Casadi`` stands
+  (``pycollo/backend.py:1341-1840``): ``create_bounds / create_scaling /
+  create_quadrature / create_initial_mesh / create_guess /
+  create_mesh_iterations / new_mesh_iteration`` (``backend.py:625-851``),
+  ``generate_nlp_function_callables`` (``:1403-1411``), ``create_nlp_solver``
+  (``:1681-1693``) and the per-callback API ``evaluate_J / evaluate_g /
+  evaluate_c / evaluate_G / evaluate_G_nonzeros / evaluate_G_structure /
+  evaluate_G_num_nonzero`` (``:1713-1771``) plus the four ``evaluate_H*`` the
+  reference leaves as ``NotImplementedError`` (``:1773-1805``).
+* ``Iteration`` mirrors ``pycollo/iteration.py:18-653`` up to (not including)
+  ``solve``: guess interpolation ``:86-194``, counts and slices ``:196-342``,
+  scaling ``:344-373``, NLP generation ``:375-394``, bounds ``:396-453``.
+* ``IterationScaling`` mirrors ``pycollo/scaling.py:124-454`` with the
+  constraint scaling computed from the *sparse* Jacobian (row norms over the
+  CCS values) instead of the dense ``np.array(G)`` of ``scaling.py:394``.
+
+All numbers come from the CUDA engine (``engine.py`` -> ``libpcx.so``); nothing
+here evaluates the NLP functions on the CPU.
+"""
+from __future__ import annotations
+
+from timeit import default_timer as timer
+from types import SimpleNamespace
+
+import numpy as np
+import scipy.sparse as sparse
+
+from . import codegen, engine as _engine
+from .derivs import analyse_phase, analyse_point
+from .mesh import Mesh, PhaseMeshData
+from .quadrature import Quadrature
+from .structure import NLPStructure
+from .symbolic import build_ir
+
+NlpResult = SimpleNamespace
+
+
+def lower_problem(ocp, meshes=None, **structure_kwargs):
+    """Symbolic lowering + structure + generated header for one mesh."""
+    ir = build_ir(ocp)
+    pds = [analyse_phase(ph, ir.s) for ph in ir.phases]
+    ptd = analyse_point(ir)
+    if meshes is None:
+        quad = Quadrature(ocp.settings.quadrature_method)
+        meshes = [PhaseMeshData(quad, ph.mesh, 2, 16) for ph in ocp.phases]
+    S = NLPStructure(ir, pds, ptd, meshes,
+                     prune=ocp.settings.prune_zero_quadrature_coefficients,
+                     **structure_kwargs)
+    header, layouts = codegen.generate(ir, pds, ptd, S)
+    return SimpleNamespace(ir=ir, pds=pds, ptd=ptd, S=S, header=header,
+                           layouts=layouts, meshes=meshes)
+
+
+class Bounds:
+    """Numeric variable bounds in OCP ordering (``pycollo/bounds.py:414-454``)."""
+
+    def __init__(self, ir):
+        rows = []
+        for ph in ir.phases:
+            rows += [ph.y_bnd, ph.u_bnd, ph.q_bnd, ph.t_bnd]
+        rows.append(ir.s_bnd)
+        self.x_bnd = np.vstack([r.reshape(-1, 2) for r in rows])
+        self.y_t0_bnd = [ph.y_t0_bnd for ph in ir.phases]
+        self.y_tF_bnd = [ph.y_tF_bnd for ph in ir.phases]
+
+    x_bnd_lower = property(lambda self: self.x_bnd[:, 0])
+    x_bnd_upper = property(lambda self: self.x_bnd[:, 1])
+
+
+class Scaling:
+    """OCP-level stretch/shift (``pycollo/scaling.py:66-115``)."""
+
+    def __init__(self, backend):
+        method = backend.ocp.settings.scaling_method
+        if method in (None, "none"):
+            n = backend.num_var
+            self.x_scales, self.x_shifts = np.ones(n), np.zeros(n)
+        else:
+            lo, hi = backend.bounds.x_bnd_lower, backend.bounds.x_bnd_upper
+            self.x_scales = hi - lo
+            self.x_shifts = hi - (hi - lo) / 2
+
+
+class Guess:
+    """Initial guess in OCP ordering (``pycollo/guess.py:117-200``)."""
+
+    def __init__(self, backend):
+        ir = backend.ir
+        self.tau, self.t0, self.tF, self.y, self.u, self.q, self.t = ([] for _ in range(7))
+        for ph, uph in zip(ir.phases, backend.ocp.phases):
+            g = uph.guess
+            if g.time is None:
+                raise ValueError("A guess must be supplied.")
+            time = np.asarray(g.time, dtype=np.float64)
+            if time.ndim != 1:
+                raise ValueError("Time guess must be a 1d array.")
+            t0, tF = time[0], time[-1]
+            stretch, shift = 0.5 * (tF - t0), 0.5 * (t0 + tF)
+            self.tau.append((time - shift) / stretch)
+            self.t0.append(t0)
+            self.tF.append(tF)
+            y = self._check(g.state_variables, len(uph.state_variables), time.size)
+            u = self._check(g.control_variables, len(uph.control_variables), time.size)
+            q = self._check(g.integral_variables, len(uph.integral_variables))
+            self.y.append(y[ph.y_needed])
+            self.u.append(u[ph.u_needed])
+            self.q.append(q[ph.q_needed])
+            self.t.append(np.array([t0, tF])[np.array(ph.t_needed, dtype=bool)])
+        s = self._check(backend.ocp.guess.parameter_variables,
+                        len(backend.ocp.parameter_variables))
+        self.s = s[ir.s_needed] if len(s) else s
+
+    @staticmethod
+    def _check(guess, num_var, num_t=None):
+        if guess is None or num_var == 0:
+            if num_var != 0:
+                raise ValueError("A guess must be supplied.")
+            return np.empty((0, num_t)) if num_t is not None else np.empty((0,))
+        guess = np.asarray(guess, dtype=np.float64)
+        if num_t is not None:
+            if guess.shape != (num_var, num_t):
+                raise ValueError("A guess must be supplied for every symbol and time.")
+        else:
+            guess = guess.reshape(-1)
+            if guess.shape != (num_var,):
+                raise ValueError("A guess must be supplied for every symbol.")
+        return guess
+
+
+class IterationScaling:
+    """Mesh-expanded V, r and the objective/constraint scaling of one iteration."""
+
+    def __init__(self, iteration):
+        self.iteration = iteration
+        self.backend = iteration.backend
+        base = self.backend.scaling
+        self.V_ocp = base.x_scales.copy()
+        self.r_ocp = base.x_shifts.copy()
+        self.V = self._expand_x_to_mesh(self.V_ocp)
+        self.r = self._expand_x_to_mesh(self.r_ocp)
+        self.V_inv = np.reciprocal(self.V)
+        self.w = 1.0
+        self.W_ocp = np.ones(self.backend.num_c)
+
+    def scale_x(self, x):
+        return np.multiply(self.V_inv, (x - self.r))
+
+    def unscale_x(self, x_tilde):
+        return np.multiply(self.V, x_tilde) + self.r
+
+    def unscale_J(self, J_tilde):
+        return (1 / self.w) * J_tilde
+
+    def _expand_x_to_mesh(self, base):
+        it, S = self.iteration, self.iteration.S
+        out = np.empty(S.num_x)
+        for ph, t in zip(self.backend.ir.phases, S.ph):
+            o = t.V_off
+            nv = ph.n_y + ph.n_u
+            out[t.x_off:t.x_off + nv * t.N] = np.repeat(base[o["y"]:o["y"] + nv], t.N)
+            out[t.q_col:t.q_col + ph.n_q] = base[o["q"]:o["q"] + ph.n_q]
+            out[t.q_col + ph.n_q:t.q_col + ph.n_q + ph.n_t] = \
+                base[o["t"]:o["t"] + ph.n_t]
+        out[S.s_off:] = base[S.s_ocp_off:S.s_ocp_off + S.NS]
+        return out
+
+    def _expand_c_to_mesh(self, base):
+        S = self.iteration.S
+        out = np.empty(S.num_c)
+        for ph, t in zip(self.backend.ir.phases, S.ph):
+            nd = ph.n_y * (t.N - 1)
+            out[t.c_off:t.c_off + nd] = np.repeat(base[t.W_off:t.W_off + ph.n_y], t.N - 1)
+            out[t.c_off + nd:t.c_off + nd + ph.n_p * t.N] = \
+                np.repeat(base[t.W_off + ph.n_y:t.W_off + ph.n_y + ph.n_p], t.N)
+            out[t.c_off + nd + ph.n_p * t.N:t.c_off + nd + ph.n_p * t.N + ph.n_q] = \
+                base[t.W_off + ph.n_y + ph.n_p:t.W_off + ph.n_y + ph.n_p + ph.n_q]
+        out[S.b_off:] = base[S.Wb_off:S.Wb_off + S.NB]
+        return out
+
+    @property
+    def W(self):
+        return self._expand_c_to_mesh(self.W_ocp)
+
+    def generate_J_c_scaling(self):
+        """``pycollo/scaling.py:204-210, 261-275, 346-430`` with sparse row norms."""
+        it = self.iteration
+        method = self.backend.ocp.settings.scaling_method
+        if method in (None, "none"):
+            self.w, self.W_ocp = 1.0, np.ones(self.backend.num_c)
+            it.push_scaling()
+            return
+        # evaluate g and G at the guess with unit scaling (w = 1, W = 1)
+        self.w, self.W_ocp = 1.0, np.ones(self.backend.num_c)
+        it.push_scaling()
+        x0 = it.guess_x_tilde
+        if it.number == 1:
+            w = 1.0
+        else:
+            g = it.evaluate(_engine.EVAL_GRAD, x0)["grad"][0]
+            g_norm = np.sqrt(np.sum(g ** 2))
+            w = 1.0 if np.isclose(g_norm, 0.0) else 1.0 / g_norm
+        vals = it.evaluate(_engine.EVAL_JAC, x0)["jac"][0]
+        rows, _ = it.S.G_structure()
+        G_norm = np.sqrt(np.bincount(rows, vals * vals, minlength=it.S.num_c))
+        W = np.empty(self.backend.num_c)
+        S = it.S
+        for ph, t in zip(self.backend.ir.phases, S.ph):
+            o = t.V_off
+            W[t.W_off:t.W_off + ph.n_y] = np.reciprocal(self.V_ocp[o["y"]:o["y"] + ph.n_y])
+            p0 = t.c_off + ph.n_y * (t.N - 1)
+            if ph.n_p:
+                W[t.W_off + ph.n_y:t.W_off + ph.n_y + ph.n_p] = np.reciprocal(
+                    np.mean(G_norm[p0:p0 + ph.n_p * t.N].reshape(ph.n_p, t.N), axis=1))
+            W[t.W_off + ph.n_y + ph.n_p:t.W_off + ph.n_y + ph.n_p + ph.n_q] = \
+                np.reciprocal(self.V_ocp[o["q"]:o["q"] + ph.n_q])
+        W[S.Wb_off:] = np.reciprocal(G_norm[S.b_off:])
+        self.w, self.W_ocp = w, W
+        it.push_scaling()
+
+
+class Iteration:
+    """One mesh iteration = one NLP (``pycollo/iteration.py:18-653``)."""
+
+    def __init__(self, backend, index, mesh, guess, batch=1, device=0):
+        self.backend = backend
+        self.ocp = backend.ocp
+        self.index = index
+        self.number = index + 1
+        self.mesh = mesh
+        self.prev_guess = guess
+        self.batch = batch
+        self.device = device
+        self.engine = None
+        self.initialise()
+
+    # -- initialise (iteration.py:69-79) ----------------------------------
+    def initialise(self):
+        t0 = timer()
+        low = lower_problem(self.ocp, self.mesh.p)
+        self.low, self.S = low, low.S
+        self.interpolate_guess_to_mesh(self.prev_guess)
+        self.create_variable_constraint_counts_slices()
+        self.scaling = IterationScaling(self)
+        self.guess_x_tilde = self.scaling.scale_x(self.guess_x)
+        self.generate_bounds()
+        self._time_initialise = timer() - t0
+
+    def interpolate_guess_to_mesh(self, prev):
+        """Linear interpolation of the previous guess (``iteration.py:86-194``)."""
+        self.guess_tau = self.mesh.tau
+        parts = []
+        self.guess_y, self.guess_u = [], []
+        for ip, (tau, ptau) in enumerate(zip(self.mesh.tau, prev.tau)):
+            y = np.vstack([np.interp(tau, ptau, row) for row in prev.y[ip]]) \
+                if len(prev.y[ip]) else np.empty((0, len(tau)))
+            u = np.vstack([np.interp(tau, ptau, row) for row in prev.u[ip]]) \
+                if len(prev.u[ip]) else np.empty((0, len(tau)))
+            self.guess_y.append(y)
+            self.guess_u.append(u)
+            parts += [y.ravel(), u.ravel(), np.ravel(prev.q[ip]), np.ravel(prev.t[ip])]
+        parts.append(np.ravel(prev.s))
+        self.guess_x = np.concatenate(parts).astype(np.float64)
+
+    def create_variable_constraint_counts_slices(self):
+        """``iteration.py:196-342``."""
+        S, ir = self.S, self.backend.ir
+        self.num_x, self.num_c = S.num_x, S.num_c
+        self.y_slices, self.u_slices, self.q_slices, self.t_slices = [], [], [], []
+        self.x_slices, self.c_defect_slices, self.c_path_slices = [], [], []
+        self.c_integral_slices, self.c_slices, self.dy_slices = [], [], []
+        for ph, t in zip(ir.phases, S.ph):
+            y0 = t.x_off
+            u0 = y0 + ph.n_y * t.N
+            self.y_slices.append(slice(y0, u0))
+            self.u_slices.append(slice(u0, t.q_col))
+            self.q_slices.append(slice(t.q_col, t.q_col + ph.n_q))
+            self.t_slices.append(slice(t.q_col + ph.n_q, t.q_col + ph.n_q + ph.n_t))
+            self.x_slices.append(slice(y0, t.q_col + ph.n_q + ph.n_t))
+            d1 = t.c_off + ph.n_y * (t.N - 1)
+            p1 = d1 + ph.n_p * t.N
+            self.c_defect_slices.append(slice(t.c_off, d1))
+            self.c_path_slices.append(slice(d1, p1))
+            self.c_integral_slices.append(slice(p1, p1 + ph.n_q))
+            self.c_slices.append(slice(t.c_off, p1 + ph.n_q))
+            self.dy_slices.append(slice(t.dy_off, t.dy_off + ph.n_y * t.N))
+        self.s_slice = slice(S.s_off, S.num_x)
+        self.c_endpoint_slice = slice(S.b_off, S.num_c)
+        self.num_s = S.NS
+
+    def generate_bounds(self):
+        """x and c bounds on the mesh (``iteration.py:396-453``): state endpoint
+        constraints are *variable bounds*, not rows of c (``:419-420``)."""
+        S, ir = self.S, self.backend.ir
+        sc = self.scaling
+        lo = np.empty(S.num_x)
+        hi = np.empty(S.num_x)
+        for ph, t in zip(ir.phases, S.ph):
+            for i in range(ph.n_y):
+                sl = slice(t.x_off + i * t.N, t.x_off + (i + 1) * t.N)
+                lo[sl], hi[sl] = ph.y_bnd[i]
+                lo[sl.start], hi[sl.start] = ph.y_t0_bnd[i]
+                lo[sl.stop - 1], hi[sl.stop - 1] = ph.y_tF_bnd[i]
+            for j in range(ph.n_u):
+                sl = slice(t.x_off + (ph.n_y + j) * t.N, t.x_off + (ph.n_y + j + 1) * t.N)
+                lo[sl], hi[sl] = ph.u_bnd[j]
+            lo[t.q_col:t.q_col + ph.n_q] = ph.q_bnd[:, 0]
+            hi[t.q_col:t.q_col + ph.n_q] = ph.q_bnd[:, 1]
+            lo[t.q_col + ph.n_q:t.q_col + ph.n_q + ph.n_t] = ph.t_bnd[:, 0]
+            hi[t.q_col + ph.n_q:t.q_col + ph.n_q + ph.n_t] = ph.t_bnd[:, 1]
+        lo[S.s_off:] = ir.s_bnd[:, 0]
+        hi[S.s_off:] = ir.s_bnd[:, 1]
+        self.x_bnd_l = sc.scale_x(lo)
+        self.x_bnd_u = sc.scale_x(hi)
+        cl = np.zeros(S.num_c)
+        cu = np.zeros(S.num_c)
+        for ph, t, sl in zip(ir.phases, S.ph, self.c_path_slices):
+            if ph.n_p:
+                cl[sl] = np.repeat(ph.p_bnd[:, 0], t.N)
+                cu[sl] = np.repeat(ph.p_bnd[:, 1], t.N)
+        cl[S.b_off:] = ir.b_bnd[:, 0]
+        cu[S.b_off:] = ir.b_bnd[:, 1]
+        self._c_bnd_unscaled = (cl, cu)
+
+    @property
+    def c_bnd_l(self):
+        return self.scaling.W * self._c_bnd_unscaled[0]
+
+    @property
+    def c_bnd_u(self):
+        return self.scaling.W * self._c_bnd_unscaled[1]
+
+    # -- the engine --------------------------------------------------------
+    def generate_nlp(self):
+        """``iteration.py:375-394``: compile callbacks, then derive J/c scaling."""
+        t0 = timer()
+        self.backend.generate_nlp_function_callables(self)
+        self.scaling.generate_J_c_scaling()
+        self.backend.create_nlp_solver()
+        self._time_generate_nlp = timer() - t0
+
+    def create_engine(self):
+        if self.engine is None:
+            self.engine = _engine.Engine(self.S, self.low.layouts, self.low.header,
+                                         batch=self.batch, device=self.device)
+            self.push_scaling()
+        return self.engine
+
+    def push_scaling(self):
+        if self.engine is not None:
+            self.engine.set_scaling(self.scaling.V_ocp, self.scaling.r_ocp,
+                                    self.scaling.W_ocp, self.scaling.w)
+
+    def evaluate(self, what, x, lam=None, sigma=None):
+        return self.create_engine().eval_host(what, x, lam, sigma)
+
+
+class Cuda:
+    """The ``backend="cuda"`` object held as ``ocp._backend``."""
+
+    def __init__(self, ocp):
+        self.ocp = ocp
+        self.ir = build_ir(ocp)
+        self.p = self.ir.phases
+        self.num_phases = len(self.p)
+        self.num_var = sum(ph.n_y + ph.n_u + ph.n_q + ph.n_t for ph in self.p) + self.ir.n_s
+        self.num_c = sum(ph.n_y + ph.n_p + ph.n_q for ph in self.p) + self.ir.n_b
+        self.num_s_var = self.ir.n_s
+        self.num_b_con = self.ir.n_b
+        self.mesh_iterations = []
+        self.current_iteration = None
+        self._slices()
+
+    def _slices(self):
+        """OCP-level slices (``pycollo/backend.py:664-704, 781-816``)."""
+        self.phase_y_var_slices, self.phase_u_var_slices = [], []
+        self.phase_q_var_slices, self.phase_t_var_slices = [], []
+        self.phase_variable_slices = []
+        self.phase_y_eqn_slices, self.phase_p_con_slices = [], []
+        self.phase_q_fnc_slices, self.phase_c_slices = [], []
+        v = c = 0
+        for ph in self.p:
+            self.phase_y_var_slices.append(slice(v, v + ph.n_y))
+            self.phase_u_var_slices.append(slice(v + ph.n_y, v + ph.n_y + ph.n_u))
+            q0 = v + ph.n_y + ph.n_u
+            self.phase_q_var_slices.append(slice(q0, q0 + ph.n_q))
+            self.phase_t_var_slices.append(slice(q0 + ph.n_q, q0 + ph.n_q + ph.n_t))
+            self.phase_variable_slices.append(slice(v, q0 + ph.n_q + ph.n_t))
+            v = q0 + ph.n_q + ph.n_t
+            self.phase_y_eqn_slices.append(slice(c, c + ph.n_y))
+            self.phase_p_con_slices.append(slice(c + ph.n_y, c + ph.n_y + ph.n_p))
+            self.phase_q_fnc_slices.append(
+                slice(c + ph.n_y + ph.n_p, c + ph.n_y + ph.n_p + ph.n_q))
+            self.phase_c_slices.append(slice(c, c + ph.n_y + ph.n_p + ph.n_q))
+            c += ph.n_y + ph.n_p + ph.n_q
+        self.s_var_slice = slice(v, v + self.ir.n_s)
+        self.c_endpoint_slice = slice(c, c + self.ir.n_b)
+
+    # -- construction steps (optimal_control_problem.py:316-337) ----------
+    def create_bounds(self):
+        self.bounds = Bounds(self.ir)
+
+    def create_scaling(self):
+        self.scaling = Scaling(self)
+
+    def create_quadrature(self):
+        self.quadrature = Quadrature(self.ocp.settings.quadrature_method)
+
+    def postprocess_problem_backend(self):
+        pass
+
+    def create_initial_mesh(self):
+        s = self.ocp.settings
+        self.initial_mesh = Mesh(self.quadrature, [ph.mesh for ph in self.ocp.phases],
+                                 s.collocation_points_min, s.collocation_points_max)
+
+    def create_guess(self):
+        self.initial_guess = Guess(self)
+
+    def create_mesh_iterations(self):
+        self.mesh_iterations = []
+        self.new_mesh_iteration(self.initial_mesh, self.initial_guess)
+
+    def new_mesh_iteration(self, mesh, guess, batch=1, device=0):
+        it = Iteration(self, len(self.mesh_iterations), mesh, guess, batch, device)
+        self.mesh_iterations.append(it)
+        self.current_iteration = it
+        return it
+
+    def iteration_scaling(self, iteration):
+        return IterationScaling(iteration)
+
+    # -- NLP function generation (backend.py:1403-1411, 1681-1693) --------
+    def generate_nlp_function_callables(self, iteration):
+        self.current_iteration = iteration
+        iteration.create_engine()
+
+    def create_nlp_solver(self):
+        """No IPOPT in this image: the 'solver' is the cyipopt-style callback
+        object a host NLP solver consumes (``pycollo/nlp.py:36-76``)."""
+        self.nlp_solver = self.nlp_callbacks()
+        return self.nlp_solver
+
+    # -- per-callback API (backend.py:1713-1805) ----------------------------
+    def _it(self):
+        if self.current_iteration is None:
+            raise RuntimeError("no mesh iteration has been created")
+        return self.current_iteration
+
+    def evaluate_J(self, x):
+        return float(self._it().evaluate(_engine.EVAL_F, x)["f"][0])
+
+    def evaluate_g(self, x):
+        return self._it().evaluate(_engine.EVAL_GRAD, x)["grad"][0]
+
+    def evaluate_c(self, x):
+        return self._it().evaluate(_engine.EVAL_C, x)["c"][0]
+
+    def evaluate_dy(self, x):
+        return self._it().evaluate(_engine.EVAL_DY, x)["dy"][0]
+
+    dy_iter_callable = evaluate_dy
+
+    def evaluate_G_nonzeros(self, x):
+        return self._it().evaluate(_engine.EVAL_JAC, x)["jac"][0]
+
+    def evaluate_G_structure(self):
+        rows, cols = self._it().S.G_structure()
+        return rows.copy(), cols.copy()
+
+    def evaluate_G_num_nonzero(self):
+        return int(self._it().S.nnz_g)
+
+    def evaluate_G(self, x):
+        it = self._it()
+        rows, cols = it.S.G_structure()
+        return sparse.coo_matrix((self.evaluate_G_nonzeros(x), (rows, cols)),
+                                 shape=(it.S.num_c, it.S.num_x))
+
+    def evaluate_H_nonzeros(self, x, obj_factor=1.0, lagrange=None):
+        it = self._it()
+        if lagrange is None:
+            lagrange = np.zeros(it.S.num_c)
+        return it.evaluate(_engine.EVAL_HESS, x, lagrange, obj_factor)["hess"][0]
+
+    def evaluate_H_structure(self):
+        rows, cols = self._it().S.H_structure()
+        return rows.copy(), cols.copy()
+
+    def evaluate_H_num_nonzero(self):
+        return int(self._it().S.nnz_h)
+
+    def evaluate_H(self, x, obj_factor=1.0, lagrange=None):
+        it = self._it()
+        rows, cols = it.S.H_structure()
+        return sparse.coo_matrix(
+            (self.evaluate_H_nonzeros(x, obj_factor, lagrange), (rows, cols)),
+            shape=(it.S.num_x, it.S.num_x))
+
+    def nlp_callbacks(self):
+        from .nlp import NlpCallbacks
+        return NlpCallbacks(self._it())
+
+    def solve_nlp(self):
+        raise NotImplementedError(
+            "No host NLP solver (IPOPT) is available in this environment; "
+            "use Cuda.nlp_callbacks() with cyipopt - see INTEGRATION.md.")

@@ -1,0 +1,303 @@
+"""CUDA code generation for the per-node expression bodies.
+
+Only the *expression bodies* are generated (task brief / BASELINE north star):
+for each phase one ``__device__`` function evaluating, at one collocation node,
+the state equations / path constraints / integrands, their structural first
+derivatives and the multiplier-contracted second derivatives, from a common
+sub-expression-eliminated straight-line program (``sympy.cse``) -- the same
+idea as the reference's dead "tiered SSA" generator (``pycollo/numbafy.py:
+231-245``, ``expression_graph.py``), but derivative rules come from sympy, not
+from the reference's broken table.  Plus one point function
+for the objective and endpoint constraints.  The generated header also carries
+the constexpr dimension / offset tables the hand-written skeleton
+(``csrc/pcx_kernels.cuh``) is specialised on.  Kernel code is NOT generated.
+
+Mesh-dependent quantities never appear here, so a mesh refinement does not
+trigger a recompile.
+"""
+from __future__ import annotations
+
+import hashlib
+
+import sympy as sym
+from sympy.printing.c import C99CodePrinter
+
+
+class _CudaPrinter(C99CodePrinter):
+    def _print_Float(self, expr):
+        return repr(float(expr))
+
+    def _print_Integer(self, expr):
+        return f"{int(expr)}.0"
+
+    def _print_Rational(self, expr):
+        return f"({int(expr.p)}.0/{int(expr.q)}.0)"
+
+    def _print_Pow(self, expr):
+        base, exp = expr.base, expr.exp
+        if exp.is_Integer and 1 <= abs(int(exp)) <= 4:
+            b = self.parenthesize(base, 1000)
+            prod = "*".join([b] * abs(int(exp)))
+            return f"({prod})" if int(exp) > 0 else f"(1.0/({prod}))"
+        if exp == sym.Rational(1, 2):
+            return f"sqrt({self._print(base)})"
+        if exp == sym.Rational(-1, 2):
+            return f"rsqrt({self._print(base)})" if False else \
+                f"(1.0/sqrt({self._print(base)}))"
+        return f"pow({self._print(base)}, {self._print(exp)})"
+
+    def _print_Symbol(self, expr):
+        return str(expr)
+
+
+_PRINTER = _CudaPrinter()
+
+
+def _ccode(e):
+    return _PRINTER.doprint(sym.sympify(e))
+
+
+def _cfun(name, values, default=0):
+    """constexpr lookup function (arrays of static members are awkward in
+    device code; a ternary chain folds away after unrolling)."""
+    body = "".join(f"i=={k}?{int(v)}:" for k, v in enumerate(values))
+    return (f"    static __host__ __device__ constexpr int {name}(int i) "
+            f"{{ return {body}{default}; }}\n")
+
+
+def _gfun(name, values, default=0):
+    body = "".join(f"i=={k}?{int(v)}:" for k, v in enumerate(values))
+    return (f"__host__ __device__ constexpr int {name}(int i) "
+            f"{{ return {body}{default}; }}\n")
+
+
+def _emit_program(inputs, outputs, indent="        "):
+    """Straight-line program: ``inputs`` = [(symbol, c_expr)], ``outputs`` =
+    [(c_lvalue, sympy expr)].  Shared CSE across all outputs; sin/cos of the
+    same argument fused into one ``sincos``."""
+    lines = []
+    exprs = [sym.sympify(e) for _, e in outputs]
+    # fuse sin/cos pairs on trig-free arguments
+    trig_args = {}
+    for e in exprs:
+        for node in e.atoms(sym.sin, sym.cos):
+            arg = node.args[0]
+            if not arg.has(sym.sin, sym.cos):
+                trig_args.setdefault(arg, set()).add(type(node))
+    pre = []
+    trig_sub = {}
+    for k, (arg, kinds) in enumerate(sorted(trig_args.items(),
+                                            key=lambda kv: sym.default_sort_key(kv[0]))):
+        s_sym, c_sym = sym.Symbol(f"sn{k}"), sym.Symbol(f"cs{k}")
+        if kinds == {sym.sin, sym.cos}:
+            pre.append(f"{indent}double sn{k}, cs{k}; sincos({_ccode(arg)}, &sn{k}, &cs{k});")
+            trig_sub[sym.sin(arg)] = s_sym
+            trig_sub[sym.cos(arg)] = c_sym
+        elif kinds == {sym.sin}:
+            pre.append(f"{indent}const double sn{k} = sin({_ccode(arg)});")
+            trig_sub[sym.sin(arg)] = s_sym
+        else:
+            pre.append(f"{indent}const double cs{k} = cos({_ccode(arg)});")
+            trig_sub[sym.cos(arg)] = c_sym
+    if trig_sub:
+        exprs = [e.xreplace(trig_sub) for e in exprs]
+    repl, reduced = sym.cse(exprs, symbols=sym.numbered_symbols("w_"),
+                            order="none")
+    for s, cexpr in inputs:
+        lines.append(f"{indent}const double {s} = {cexpr};")
+    lines.extend(pre)
+    for s, e in repl:
+        lines.append(f"{indent}const double {s} = {_ccode(e)};")
+    for (lv, _), e in zip(outputs, reduced):
+        lines.append(f"{indent}{lv} = {_ccode(e)};")
+    return "\n".join(lines)
+
+
+class PhaseLayout:
+    """Offsets of the per-phase runtime tables (pscal: doubles, pbase: int64)."""
+
+    def __init__(self, pd, has_t0, has_tF, pscal_off, pbase_off):
+        NV, NF, NY = pd.NV, pd.NF, pd.NY
+        self.pd = pd
+        self.has_t0, self.has_tF = has_t0, has_tF
+        o = 0
+        self.ps = {}
+        for name, n in (("VV", NV), ("RV", NV), ("WFN", NF), ("D1V", len(pd.d1v)),
+                        ("D1S", len(pd.d1s)), ("GCST", 1 + 2 * NY),
+                        ("H2VV", len(pd.h2vv)), ("H2VS", len(pd.h2vs)),
+                        ("HT0", len(pd.htv)), ("HTF", len(pd.htv)),
+                        ("GT0", NY), ("GTF", NY), ("TINFO", 4)):
+            self.ps[name] = o
+            o += n
+        self.pscal_size = o
+        self.pscal_off = pscal_off
+        o = 0
+        self.pb = {}
+        for name, n in (("N", 1), ("K", 1), ("XOFF", 1), ("COFF", 1), ("DYOFF", 1),
+                        ("SECOFF", 1), ("GSECOFF", 1), ("T0X", 1), ("TFX", 1),
+                        ("TILE0", 1), ("TILE1", 1), ("IRR0", 1), ("IRR1", 1),
+                        ("GT0", NY), ("GTF", NY), ("GSCOL", len(pd.d1s)),
+                        ("HREG", NV), ("HS", len(pd.h2vs)),
+                        ("HT0", len(pd.htv)), ("HTF", len(pd.htv))):
+            self.pb[name] = o
+            o += n
+        self.pbase_size = o
+        self.pbase_off = pbase_off
+        # reductions (order must match structure._build_border)
+        self.red_g = 0
+        self.red_gs = pd.NQ
+        n_gs = sum(1 for e, _ in pd.d1s if pd.fam[e] == "i")
+        self.red_hts = self.red_gs + n_gs
+        self.red_hss = self.red_hts + len(pd.hts)
+        self.nred = self.red_hss + len(pd.h2ss)
+
+
+def generate(ir, phase_derivs, point_derivs, structure):
+    """Return (header_source, layouts)."""
+    P = len(ir.phases)
+    NS, NB = ir.n_s, ir.n_b
+    npt = len(point_derivs.pts)
+    out = ["// generated by pycollo_b200.codegen -- do not edit\n",
+           "#pragma once\n",
+           f"#define PCX_NUM_PHASES {P}\n#define PCX_NS {NS}\n#define PCX_NB {NB}\n",
+           f"#define PCX_NPOINT {npt}\n",
+           f"#define PCX_GS_VS 0\n#define PCX_GS_RS {NS}\n#define PCX_GS_W {2 * NS}\n"
+           f"#define PCX_GS_WB {2 * NS + 1}\n",
+           f"#define PCX_BV_PTVAL {structure.bv_ptval}\n#define PCX_BV_PTFN {structure.bv_ptfn}\n"
+           f"#define PCX_BV_PTD1 {structure.bv_ptd1}\n#define PCX_BV_PTD2 {structure.bv_ptd2}\n",
+           "#define PCX_FOREACH_PHASE(X) " + " ".join(f"X({q})" for q in range(P)) + "\n",
+           "template <int P> struct PcxPhase;\n"]
+    layouts = []
+    ps_off = pb_off = 0
+    for q, (ph, pd) in enumerate(zip(ir.phases, phase_derivs)):
+        lay = PhaseLayout(pd, ph.t_needed[0], ph.t_needed[1], ps_off, pb_off)
+        layouts.append(lay)
+        ps_off += lay.pscal_size
+        pb_off += lay.pbase_size
+        out.append(_phase_struct(q, ph, pd, lay, NS))
+    out.append(_gfun("PCX_PHASE_NRED", [l.nred for l in layouts]))
+    out.append(_gfun("PCX_PHASE_REDOFF", [t.red_off for t in structure.ph]))
+    out.append(_gfun("PCX_PHASE_PBASE", [l.pbase_off for l in layouts]))
+    out.append(_gfun("PCX_PHASE_PSCAL", [l.pscal_off for l in layouts]))
+    out.append(_gfun("PCX_PHASE_TINFO", [l.ps["TINFO"] for l in layouts]))
+    pb0 = layouts[0].pb
+    out.append(f"#define PCX_PB_T0X {pb0['T0X']}\n#define PCX_PB_TFX {pb0['TFX']}\n"
+               f"#define PCX_PB_TILE0 {pb0['TILE0']}\n#define PCX_PB_TILE1 {pb0['TILE1']}\n")
+    out.append(_point_function(point_derivs, NB))
+    src = "".join(out)
+    return src, layouts
+
+
+def _phase_struct(q, ph, pd, lay, NS):
+    NV, NF, NY = pd.NV, pd.NF, pd.NY
+    fam_code = {"d": 0, "p": 1, "i": 2}
+    pairs_by_b = {}
+    for k, (a, b) in enumerate(pd.h2vv):
+        pairs_by_b.setdefault(b, []).append((a, k))
+    pos = [0] * len(pd.h2vv)
+    nA = [0] * NV
+    for b in range(NV):
+        lst = sorted(pairs_by_b.get(b, []))
+        nA[b] = len(lst)
+        for i, (_, k) in enumerate(lst):
+            pos[k] = i
+    s = [f"template <> struct PcxPhase<{q}> {{\n",
+         f"    static constexpr int INDEX = {q};\n",
+         f"    static constexpr int NY = {NY}, NU = {pd.NU}, NV = {NV}, NP = {pd.NP}, "
+         f"NQ = {pd.NQ}, NF = {NF};\n",
+         f"    static constexpr int ND1V = {len(pd.d1v)}, ND1S = {len(pd.d1s)}, "
+         f"ND1SD = {sum(1 for e, _ in pd.d1s if pd.fam[e] == 'd')};\n",
+         f"    static constexpr int NH2VV = {len(pd.h2vv)}, NH2VS = {len(pd.h2vs)}, "
+         f"NH2SS = {len(pd.h2ss)}, NHTV = {len(pd.htv)}, NHTS = {len(pd.hts)};\n",
+         f"    static constexpr bool HAS_T0 = {'true' if lay.has_t0 else 'false'}, "
+         f"HAS_TF = {'true' if lay.has_tF else 'false'};\n",
+         f"    static constexpr int NRED = {lay.nred}, RED_G = {lay.red_g}, "
+         f"RED_GS = {lay.red_gs}, RED_HTS = {lay.red_hts}, RED_HSS = {lay.red_hss};\n",
+         f"    static constexpr int PSCAL_OFF = {lay.pscal_off}, PBASE_OFF = {lay.pbase_off};\n"]
+    for name, o in lay.ps.items():
+        s.append(f"    static constexpr int OFF_{name} = {o};\n")
+    for name, o in lay.pb.items():
+        s.append(f"    static constexpr int PB_{name} = {o};\n")
+    s.append(_cfun("FAM", [fam_code[f] for f in pd.fam]))
+    s.append(_cfun("FN_NZ", [1 if z else 0 for z in pd.fn_nonzero]))
+    s.append(_cfun("D1V_FN", [e for e, _ in pd.d1v]))
+    s.append(_cfun("D1S_FN", [e for e, _ in pd.d1s]))
+    s.append(_cfun("H2VV_B", [b for _, b in pd.h2vv]))
+    s.append(_cfun("H2VV_POS", pos))
+    s.append(_cfun("NA", nA))
+
+    # ---- the expression body ----
+    vsyms = [sym.Symbol(f"v{a}") for a in range(NV + NS)]
+    sub = dict(zip(pd.variables, vsyms))
+    muh = [sym.Symbol(f"mh{e}") for e in range(NF)]
+    mut = [sym.Symbol(f"mt{e}") for e in range(NF)]
+    outputs = []
+    for e, fe in enumerate(pd.fns):
+        outputs.append((f"F[{e}]", fe.xreplace(sub)))
+    for k, de in enumerate(pd.d1v_expr):
+        outputs.append((f"D1V[{k}]", de.xreplace(sub)))
+    for k, de in enumerate(pd.d1s_expr):
+        outputs.append((f"D1S[{k}]", de.xreplace(sub)))
+    contr = {}
+    for (e, a, b, dab) in pd.d2:
+        contr[(a, b)] = contr.get((a, b), 0) + muh[e] * dab.xreplace(sub)
+    for k, (a, b) in enumerate(pd.h2vv):
+        outputs.append((f"H2VV[{k}]", contr[(a, b)]))
+    for k, (a, j) in enumerate(pd.h2vs):
+        outputs.append((f"H2VS[{k}]", contr[(a, NV + j)]))
+    for k, (i, j) in enumerate(pd.h2ss):
+        outputs.append((f"H2SS[{k}]", contr[(NV + i, NV + j)]))
+    d1_by_var = {}
+    for (e, a), de in zip(pd.d1v, pd.d1v_expr):
+        if pd.fam[e] in "di":
+            d1_by_var[a] = d1_by_var.get(a, 0) + mut[e] * de.xreplace(sub)
+    for (e, j), de in zip(pd.d1s, pd.d1s_expr):
+        if pd.fam[e] in "di":
+            d1_by_var[NV + j] = d1_by_var.get(NV + j, 0) + mut[e] * de.xreplace(sub)
+    for k, a in enumerate(pd.htv):
+        outputs.append((f"HTV[{k}]", d1_by_var[a]))
+    for k, j in enumerate(pd.hts):
+        outputs.append((f"HTS[{k}]", d1_by_var[NV + j]))
+    inputs = [(f"v{a}", f"v[{a}]") for a in range(NV + NS)]
+    inputs += [(f"mh{e}", f"muh[{e}]") for e in range(NF)]
+    inputs += [(f"mt{e}", f"mut[{e}]") for e in range(NF)]
+    s.append("    static __device__ __forceinline__ void eval(\n"
+             "        const double* __restrict__ v, const double* __restrict__ muh,\n"
+             "        const double* __restrict__ mut, double* __restrict__ F,\n"
+             "        double* __restrict__ D1V, double* __restrict__ D1S,\n"
+             "        double* __restrict__ H2VV, double* __restrict__ H2VS,\n"
+             "        double* __restrict__ H2SS, double* __restrict__ HTV,\n"
+             "        double* __restrict__ HTS) {\n")
+    s.append(_emit_program(inputs, outputs))
+    s.append("\n    }\n};\n")
+    return "".join(s)
+
+
+def _point_function(ptd, NB):
+    npt = len(ptd.pts)
+    psyms = [sym.Symbol(f"p{a}") for a in range(npt)]
+    sub = dict(zip(ptd.pts, psyms))
+    mult = [sym.Symbol(f"m{e}") for e in range(1 + NB)]
+    outputs = []
+    for e, fe in enumerate(ptd.fns):
+        outputs.append((f"PV[{e}]", fe.xreplace(sub)))
+    for k, de in enumerate(ptd.d1_expr):
+        outputs.append((f"PD1[{k}]", de.xreplace(sub)))
+    contr = {}
+    for (e, a, b, dab) in ptd.d2:
+        contr[(a, b)] = contr.get((a, b), 0) + mult[e] * dab.xreplace(sub)
+    for k, ab in enumerate(ptd.pairs):
+        outputs.append((f"PD2[{k}]", contr[ab]))
+    inputs = [(f"p{a}", f"pt[{a}]") for a in range(npt)]
+    inputs += [(f"m{e}", f"mult[{e}]") for e in range(1 + NB)]
+    body = _emit_program(inputs, outputs, indent="    ")
+    return ("__device__ __noinline__ void pcx_point_eval(const double* pt, "
+            "const double* mult, double* PV, double* PD1, double* PD2) {\n"
+            + body + "\n}\n")
+
+
+def source_hash(*parts):
+    h = hashlib.sha256()
+    for p in parts:
+        h.update(p.encode() if isinstance(p, str) else p)
+    return h.hexdigest()[:16]

@@ -1,0 +1,61 @@
+// pcx_params.h -- kernel parameter block shared by the NVRTC-compiled skeleton
+// (pcx_kernels.cuh) and the host library (pcx_api.cu).  Plain C layout.
+#pragma once
+
+#define PCX_F_C    1
+#define PCX_F_DY   2
+#define PCX_F_G    4
+#define PCX_F_H    8
+#define PCX_F_J    16
+#define PCX_F_GRAD 32
+
+
+typedef long long i64;
+typedef unsigned int u32;
+
+// recipe word layout -- keep in sync with pycollo_b200/structure.py
+#define RC_E_BITS 9
+#define RC_B_BITS 9
+#define RC_M_BITS 4
+#define RC_C_BITS 7
+#define RC_B_SHIFT 9
+#define RC_M_SHIFT 18
+#define RC_C_SHIFT 22
+#define RC_PREV_BIT 29
+#define RC_PLAIN_BIT 30
+#define RC_SKIP_BIT 31
+
+struct PcxParams {
+    // per-call
+    const double* x;        // (batch, num_x)   scaled iterate x_tilde
+    const double* lam;      // (batch, num_c)   constraint multipliers (H)
+    const double* sigma;    // (batch)          objective factor (H); null -> 1
+    double* c;              // (batch, num_c)
+    double* dy;             // (batch, num_dy)
+    double* gj;             // (batch, nnz_g)
+    double* hs;             // (batch, nnz_h)
+    double* jval;           // (batch)
+    double* grad;           // (batch, num_x)
+    i64 num_x, num_c, num_dy, nnz_g, nnz_h;
+    int num_tiles, batch, nvmax, n_border, bv_size, nred_max, btab_len, pad0;
+    // tiles
+    const int* tile_phase; const int* tile_k0; const int* tile_k1;
+    const int* tile_uniform; const i64* tile_gbase;
+    // sections (all phases concatenated; sec_node has K+1 entries per phase)
+    const i64* sec_node; const int* sec_order; const double* sec_h;
+    const int* sec_type;
+    const i64* gsec_ptr;    // per phase NV*(K+1)
+    // recipes
+    const u32* recipes; const int* type_var_off;
+    const double* btab; const int* order_a_off; const int* order_w_off;
+    // scaling-dependent tables (rewritten by pcx_set_scaling)
+    const double* pscal; const double* gscal;
+    const i64* pbase;
+    // reductions / border
+    double* partials; u32* ticket; double* bv;
+    const int* border_grp; const i64* border_slot; const int* border_ptr;
+    const int* border_bv; const int* border_rs; const double* border_coef;
+    const i64* pt_x;        // x index of each point variable
+    const double* pt_scal;  // V then r of each point variable
+};
+

@@ -1,0 +1,339 @@
+"""ctypes binding of ``libpcx.so`` and the table marshalling around it.
+
+Python is plumbing here: it builds the integer tables (``structure.py``), the
+generated header (``codegen.py``) and the small scaling tables, hands them to
+``pcx_create`` / ``pcx_set_scaling`` (``include/pcx.h``) and then only passes
+pointers.  There is no CPU fallback: if the library cannot be loaded or the
+device is absent, evaluation raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+PCX_HOST, PCX_DEVICE = 0, 1
+EVAL_C, EVAL_DY, EVAL_JAC, EVAL_HESS, EVAL_F, EVAL_GRAD = 1, 2, 4, 8, 16, 32
+
+_LIB = None
+
+
+class PcxError(RuntimeError):
+    pass
+
+
+class _Table(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("data", ctypes.c_void_p),
+                ("bytes", ctypes.c_int64)]
+
+
+class _Spec(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int32), ("threads", ctypes.c_int32),
+                ("batch", ctypes.c_int32), ("num_tiles", ctypes.c_int32),
+                ("nvmax", ctypes.c_int32), ("n_border", ctypes.c_int32),
+                ("bv_size", ctypes.c_int32), ("nred_max", ctypes.c_int32),
+                ("btab_len", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("num_x", ctypes.c_int64), ("num_c", ctypes.c_int64),
+                ("num_dy", ctypes.c_int64), ("nnz_g", ctypes.c_int64),
+                ("nnz_h", ctypes.c_int64), ("smem_bytes", ctypes.c_int64),
+                ("problem_header", ctypes.c_char_p),
+                ("num_tables", ctypes.c_int32),
+                ("tables", ctypes.POINTER(_Table))]
+
+
+def load_library(rebuild=False):
+    """Load (building first if stale and nvcc is present) the C-ABI library."""
+    global _LIB
+    if _LIB is not None and not rebuild:
+        return _LIB
+    path = _build.LIB
+    try:
+        path = _build.build(force=rebuild)
+    except Exception as exc:                      # no nvcc: use the prebuilt .so
+        if not os.path.exists(path):
+            raise PcxError(
+                f"libpcx.so is missing and could not be built ({exc}); "
+                f"pycollo_b200 has no CPU fallback") from exc
+    lib = ctypes.CDLL(path)
+    vp, dp, i64, i32 = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    lib.pcx_version.restype = ctypes.c_char_p
+    lib.pcx_last_error.restype = ctypes.c_char_p
+    lib.pcx_last_error.argtypes = [vp]
+    lib.pcx_table_name.restype = ctypes.c_char_p
+    lib.pcx_table_name.argtypes = [i32]
+    lib.pcx_table_elem_size.argtypes = [i32]
+    lib.pcx_create.argtypes = [ctypes.POINTER(_Spec), ctypes.POINTER(vp)]
+    lib.pcx_destroy.argtypes = [vp]
+    lib.pcx_destroy.restype = None
+    lib.pcx_set_scaling.argtypes = [vp, dp, i64, dp, i64, dp, i64, dp, i64]
+    lib.pcx_eval.argtypes = [vp, i32, dp, dp, dp, dp, dp, dp, dp, dp, dp, i32, vp]
+    lib.pcx_eval_f.argtypes = [vp, dp, dp, i32, vp]
+    lib.pcx_eval_grad.argtypes = [vp, dp, dp, i32, vp]
+    lib.pcx_eval_c.argtypes = [vp, dp, dp, i32, vp]
+    lib.pcx_eval_dy.argtypes = [vp, dp, dp, i32, vp]
+    lib.pcx_eval_jac.argtypes = [vp, dp, dp, i32, vp]
+    lib.pcx_eval_hess.argtypes = [vp, dp, dp, dp, dp, i32, vp]
+    lib.pcx_eval_jac_hess.argtypes = [vp, dp, dp, dp, dp, dp, i32, vp]
+    lib.pcx_sizes.argtypes = [vp] + [ctypes.POINTER(i64)] * 5 + [ctypes.POINTER(ctypes.c_int32)]
+    lib.pcx_gather.argtypes = [vp, dp, dp, i64, dp, i32, vp]
+    lib.pcx_host_alloc.argtypes = [ctypes.POINTER(vp), i64]
+    lib.pcx_host_free.argtypes = [vp]
+    lib.pcx_launch_count.argtypes = [vp]
+    lib.pcx_launch_count.restype = i64
+    lib.pcx_synchronize.argtypes = [vp, vp]
+    lib.pcx_flush_l2.argtypes = [vp, i64, vp]
+    _LIB = lib
+    return lib
+
+
+_TABLE_DTYPES = {
+    "tile_phase": np.int32, "tile_k0": np.int32, "tile_k1": np.int32,
+    "tile_uniform": np.int32, "tile_gbase": np.int64, "sec_node": np.int64,
+    "sec_order": np.int32, "sec_h": np.float64, "sec_type": np.int32,
+    "gsec_ptr": np.int64, "recipes": np.uint32, "type_var_off": np.int32,
+    "btab": np.float64, "order_a_off": np.int32, "order_w_off": np.int32,
+    "pbase": np.int64, "border_grp": np.int32, "border_slot": np.int64,
+    "border_ptr": np.int32, "border_bv": np.int32, "border_rs": np.int32,
+    "pt_x": np.int64,
+}
+
+
+def build_tables(S, layouts):
+    """All integer / quadrature tables of one (problem, mesh) for pcx_create."""
+    t = {}
+    t["tile_phase"], t["tile_k0"], t["tile_k1"] = S.tile_phase, S.tile_k0, S.tile_k1
+    t["tile_uniform"] = S.tile_uniform
+    t["tile_gbase"] = S.tile_gbase.ravel()
+    t["sec_node"] = np.concatenate([ph.sec_node for ph in S.ph])
+    t["sec_order"] = np.concatenate([ph.sec_order for ph in S.ph])
+    t["sec_h"] = np.concatenate([ph.sec_h for ph in S.ph])
+    t["sec_type"] = np.concatenate([ph.sec_type for ph in S.ph])
+    t["gsec_ptr"] = np.concatenate([ph.gsec_ptr.ravel() for ph in S.ph])
+    t["recipes"] = S.recipe_words
+    t["type_var_off"] = S.type_var_off.ravel()
+    t["btab"] = S.btab
+    t["order_a_off"], t["order_w_off"] = S.order_a_off, S.order_w_off
+    pbase = []
+    gsec_off = 0
+    tile0 = 0
+    for ip, (ph, lay) in enumerate(zip(S.ph, layouts)):
+        pd = lay.pd
+        pb = np.full(lay.pbase_size, -1, dtype=np.int64)
+        o = lay.pb
+        ntile = int(np.sum(S.tile_phase == ip))
+        pb[o["N"]], pb[o["K"]] = ph.N, ph.K
+        pb[o["XOFF"]], pb[o["COFF"]], pb[o["DYOFF"]] = ph.x_off, ph.c_off, ph.dy_off
+        pb[o["SECOFF"]], pb[o["GSECOFF"]] = ph.sec_off, gsec_off
+        pb[o["T0X"]], pb[o["TFX"]] = ph.t_cols[0], ph.t_cols[1]
+        pb[o["TILE0"]], pb[o["TILE1"]] = tile0, tile0 + ntile
+        pb[o["IRR0"]], pb[o["IRR1"]] = ph.bv_irr[0]["vv"], ph.bv_irr[1]["vv"]
+        for i in range(pd.NY):
+            pb[o["GT0"] + i] = ph.g_tcol_base.get((0, i), -1)
+            pb[o["GTF"] + i] = ph.g_tcol_base.get((1, i), -1)
+        for k, (e, j) in enumerate(pd.d1s):
+            pb[o["GSCOL"] + k] = ph.g_scol_base.get((j, e), -1)
+        for b in range(pd.NV):
+            pb[o["HREG"] + b] = ph.h_reg_base[b]
+        for k, (a, j) in enumerate(pd.h2vs):
+            pb[o["HS"] + k] = ph.h_s_base.get((a, j), -1)
+        for k, a in enumerate(pd.htv):
+            pb[o["HT0"] + k] = ph.h_t_base.get((0, a), -1)
+            pb[o["HTF"] + k] = ph.h_t_base.get((1, a), -1)
+        pbase.append(pb)
+        gsec_off += ph.gsec_ptr.size
+        tile0 += ntile
+    t["pbase"] = np.concatenate(pbase)
+    t["border_grp"], t["border_slot"] = S.border_grp, S.border_slot
+    t["border_ptr"], t["border_bv"], t["border_rs"] = S.border_ptr, S.border_bv, S.border_rs
+    t["pt_x"] = S.pt_x
+    return {k: np.ascontiguousarray(v, dtype=_TABLE_DTYPES[k]) for k, v in t.items()}
+
+
+def scaling_tables(S, layouts, V_ocp, r_ocp, W_ocp, w):
+    """pscal / gscal / border_coef / pt_scal for pcx_set_scaling.
+
+    Reference: ``x = V*x_tilde + r`` (``pycollo/scaling.py:172-178``), constraint
+    scaling W per OCP-level constraint and objective scaling w
+    (``pycollo/backend.py:1465-1493``, ``scaling.py:346-430``)."""
+    V_ocp = np.asarray(V_ocp, dtype=np.float64)
+    r_ocp = np.asarray(r_ocp, dtype=np.float64)
+    W_ocp = np.asarray(W_ocp, dtype=np.float64)
+    ps_all = []
+    Vs = V_ocp[S.s_ocp_off:S.s_ocp_off + S.NS]
+    rs = r_ocp[S.s_ocp_off:S.s_ocp_off + S.NS]
+    for ph, lay, irp in zip(S.ph, layouts, S.ir.phases):
+        pd = lay.pd
+        ps = np.zeros(lay.pscal_size)
+        o = lay.ps
+        Vv = V_ocp[ph.V_off["y"]:ph.V_off["y"] + pd.NV]
+        rv = r_ocp[ph.V_off["y"]:ph.V_off["y"] + pd.NV]
+        Wf = W_ocp[ph.W_off:ph.W_off + pd.NF]
+        ps[o["VV"]:o["VV"] + pd.NV] = Vv
+        ps[o["RV"]:o["RV"] + pd.NV] = rv
+        ps[o["WFN"]:o["WFN"] + pd.NF] = Wf
+        for k, (e, a) in enumerate(pd.d1v):
+            ps[o["D1V"] + k] = Wf[e] * Vv[a]
+        for k, (e, j) in enumerate(pd.d1s):
+            ps[o["D1S"] + k] = Wf[e] * Vs[j]
+        for i in range(pd.NY):
+            ps[o["GCST"] + 1 + 2 * i] = Wf[i] * Vv[i]
+            ps[o["GCST"] + 2 + 2 * i] = -(Wf[i] * Vv[i])
+        for k, (a, b) in enumerate(pd.h2vv):
+            ps[o["H2VV"] + k] = Vv[a] * Vv[b]
+        for k, (a, j) in enumerate(pd.h2vs):
+            ps[o["H2VS"] + k] = Vv[a] * Vs[j]
+        Vt = [V_ocp[i] if i >= 0 else 0.0 for i in ph.t_ocp]
+        rt = [r_ocp[i] if i >= 0 else c for i, c in zip(ph.t_ocp, ph.t_const)]
+        for k, a in enumerate(pd.htv):
+            ps[o["HT0"] + k] = -0.5 * Vt[0] * Vv[a]
+            ps[o["HTF"] + k] = 0.5 * Vt[1] * Vv[a]
+        for i in range(pd.NY):
+            ps[o["GT0"] + i] = -0.5 * Vt[0] * Wf[i]
+            ps[o["GTF"] + i] = 0.5 * Vt[1] * Wf[i]
+        ps[o["TINFO"]:o["TINFO"] + 4] = [Vt[0], rt[0], Vt[1], rt[1]]
+        ps_all.append(ps)
+    pscal = np.concatenate(ps_all)
+    gscal = np.concatenate([Vs, rs, [float(w)],
+                            W_ocp[S.Wb_off:S.Wb_off + S.NB]]).astype(np.float64)
+    scales = S.sidx.vector(V_ocp, W_ocp, float(w))
+    coef = S.border_coef.evaluate(scales)
+    pt_scal = np.concatenate([V_ocp[S.pt_V], r_ocp[S.pt_V]]).astype(np.float64)
+    return pscal, gscal, coef, pt_scal
+
+
+def smem_bytes(S, layouts, threads):
+    NN, SS = S.max_tile_nodes, S.max_tile_secs
+    best = 0
+    for lay in layouts:
+        pd = lay.pd
+        nds = sum(1 for e, _ in pd.d1s if pd.fam[e] == "d")
+        dbl = (len(S.btab) + SS + 1 + (pd.NY + len(pd.d1v) + nds) * (NN | 1)
+               + pd.NY * (NN + 16) + threads // 32 + 2)
+        ints = (SS + 2) + (SS + 1) + SS + NN + pd.NV * (SS + 1) + pd.NV * SS + 4
+        best = max(best, 8 * dbl + 4 * ints)
+    return int((best + 15) // 16 * 16)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(ctypes.c_void_p)
+    if hasattr(a, "data_ptr"):                  # torch tensor
+        return ctypes.c_void_p(a.data_ptr())
+    return ctypes.c_void_p(int(a))
+
+
+class Engine:
+    """One compiled problem on one mesh on one device (wraps ``pcx_engine``)."""
+
+    def __init__(self, S, layouts, header, *, batch=1, device=0):
+        self.lib = load_library()
+        self.S, self.layouts = S, layouts
+        self.batch = int(batch)
+        self.device = int(device)
+        self.threads = int(S.threads)
+        self.tables = build_tables(S, layouts)
+        self.smem = smem_bytes(S, layouts, self.threads)
+        if self.smem > 227 * 1024:
+            raise PcxError(f"tile needs {self.smem} B of shared memory (> 227 KB)")
+        n = self.lib.pcx_table_count()
+        arr = (_Table * n)()
+        self._keep = []
+        for i in range(n):
+            name = self.lib.pcx_table_name(i)
+            a = self.tables[name.decode()]
+            assert a.itemsize == self.lib.pcx_table_elem_size(i), name
+            self._keep.append(a)
+            arr[i] = _Table(name, a.ctypes.data_as(ctypes.c_void_p), a.nbytes)
+        self._header = header.encode()
+        spec = _Spec(device=self.device, threads=self.threads, batch=self.batch,
+                     num_tiles=S.num_tiles, nvmax=S.NVMAX,
+                     n_border=len(S.border_grp), bv_size=S.bv_size,
+                     nred_max=max([l.nred for l in layouts] + [1]),
+                     btab_len=len(S.btab), reserved=0,
+                     num_x=S.num_x, num_c=S.num_c, num_dy=S.num_dy,
+                     nnz_g=S.nnz_g, nnz_h=S.nnz_h, smem_bytes=self.smem,
+                     problem_header=self._header, num_tables=n, tables=arr)
+        h = ctypes.c_void_p()
+        rc = self.lib.pcx_create(ctypes.byref(spec), ctypes.byref(h))
+        if rc != 0:
+            raise PcxError(f"pcx_create failed ({rc}): "
+                           f"{self.lib.pcx_last_error(None).decode(errors='replace')}")
+        self.h = h
+
+    def __del__(self):
+        h = getattr(self, "h", None)
+        if h:
+            self.lib.pcx_destroy(h)
+            self.h = None
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.pcx_last_error(self.h).decode(errors="replace")
+            raise PcxError(f"{what} failed ({rc}): {msg}")
+
+    def set_scaling(self, V_ocp, r_ocp, W_ocp, w):
+        ps, gs, bc, pt = scaling_tables(self.S, self.layouts, V_ocp, r_ocp, W_ocp, w)
+        self._scal = (ps, gs, bc, pt)
+        self._check(self.lib.pcx_set_scaling(
+            self.h, _ptr(ps), ps.size, _ptr(gs), gs.size, _ptr(bc), bc.size,
+            _ptr(pt), pt.size), "pcx_set_scaling")
+
+    # -- host-space convenience (numpy in / numpy out) ---------------------
+    def eval_host(self, what, x, lam=None, sigma=None):
+        S, B = self.S, self.batch
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(B, S.num_x)
+        lam_ = None if lam is None else \
+            np.ascontiguousarray(lam, dtype=np.float64).reshape(B, S.num_c)
+        sig_ = None if sigma is None else \
+            np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, dtype=np.float64),
+                                                 (B,)))
+        out = {}
+        if what & EVAL_F:
+            out["f"] = np.empty(B)
+        if what & EVAL_GRAD:
+            out["grad"] = np.empty((B, S.num_x))
+        if what & EVAL_C:
+            out["c"] = np.empty((B, S.num_c))
+        if what & EVAL_DY:
+            out["dy"] = np.empty((B, S.num_dy))
+        if what & EVAL_JAC:
+            out["jac"] = np.empty((B, S.nnz_g))
+        if what & EVAL_HESS:
+            out["hess"] = np.empty((B, S.nnz_h))
+        self._check(self.lib.pcx_eval(
+            self.h, what, _ptr(x), _ptr(lam_), _ptr(sig_), _ptr(out.get("f")),
+            _ptr(out.get("grad")), _ptr(out.get("c")), _ptr(out.get("dy")),
+            _ptr(out.get("jac")), _ptr(out.get("hess")), PCX_HOST, None), "pcx_eval")
+        return out
+
+    # -- raw pointers (device tensors, pinned buffers) ------------------------
+    def eval_ptr(self, what, x, lam=None, sigma=None, f=None, grad=None, c=None,
+                 dy=None, jac=None, hess=None, space=PCX_DEVICE, stream=None):
+        self._check(self.lib.pcx_eval(
+            self.h, what, _ptr(x), _ptr(lam), _ptr(sigma), _ptr(f), _ptr(grad),
+            _ptr(c), _ptr(dy), _ptr(jac), _ptr(hess), space,
+            ctypes.c_void_p(stream) if stream else None), "pcx_eval")
+
+    def gather(self, src, perm, n, dst, stream=None):
+        self._check(self.lib.pcx_gather(self.h, _ptr(src), _ptr(perm), n, _ptr(dst),
+                                        PCX_DEVICE,
+                                        ctypes.c_void_p(stream) if stream else None),
+                    "pcx_gather")
+
+    def flush_l2(self, nbytes=256 << 20, stream=None):
+        self._check(self.lib.pcx_flush_l2(
+            self.h, nbytes, ctypes.c_void_p(stream) if stream else None),
+            "pcx_flush_l2")
+
+    def synchronize(self, stream=None):
+        self._check(self.lib.pcx_synchronize(
+            self.h, ctypes.c_void_p(stream) if stream else None), "pcx_synchronize")
+
+    @property
+    def launch_count(self):
+        return int(self.lib.pcx_launch_count(self.h))

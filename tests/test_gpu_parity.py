@@ -1,0 +1,157 @@
+"""GPU parity: CUDA engine (through the C ABI) vs the CPU oracle, same inputs.
+
+Tolerance is the one BASELINE.json's north_star states for fp64 values:
+1e-12 relative (measured against max(|ref|, 1e-2*scale) so entries that are
+pure cancellation noise are judged in units of the vector's scale); sparsity
+indices are compared bit-exactly in the CPU tests (tests/test_structure.py).
+"""
+import numpy as np
+import pytest
+
+from helpers import (RAGGED_NODES, RAGGED_SIZES, build_case, make_engine, max_err)
+from pycollo_b200 import engine as E
+from pycollo_b200 import examples
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+ALL = E.EVAL_C | E.EVAL_DY | E.EVAL_JAC | E.EVAL_HESS | E.EVAL_F | E.EVAL_GRAD
+
+CASES = [
+    ("brachistochrone", "lobatto", 10, 4, None, {}),
+    ("brachistochrone", "radau", 10, 4, None, {}),
+    ("cart_pole_swing_up", "lobatto", 10, 4, None, {}),
+    ("cart_pole_swing_up", "radau", 40, 4, None, dict(max_tile_nodes=16)),
+    ("hypersensitive", "lobatto", 6, RAGGED_NODES, RAGGED_SIZES, dict(max_tile_nodes=20)),
+    ("hypersensitive", "radau", 6, RAGGED_NODES, RAGGED_SIZES, {}),
+    ("double_pendulum", "lobatto", 6, RAGGED_NODES, RAGGED_SIZES, dict(max_tile_nodes=20)),
+    ("double_pendulum", "radau", 10, 4, None, {}),
+    ("cart_pole_swing_up", "lobatto", 2000, 4, None, {}),
+]
+
+
+def _check(out, B, x, lam, sigma):
+    errs = dict(
+        f=max_err(out["f"], [B.J(x)]), grad=max_err(out["grad"][0], B.g(x)),
+        c=max_err(out["c"][0], B.c(x)), dy=max_err(out["dy"][0], B.dy(x)),
+        jac=max_err(out["jac"][0], B.G_nonzeros(x)),
+        hess=max_err(out["hess"][0], B.H_nonzeros(x, sigma, lam)))
+    bad = {k: v for k, v in errs.items() if not v <= RTOL}
+    assert not bad, f"parity violated: {bad} (all: {errs})"
+
+
+@pytest.mark.parametrize("name,method,K,nodes,sizes,kw", CASES)
+def test_all_callbacks_match_oracle(cuda_device, name, method, K, nodes, sizes, kw):
+    ocp = getattr(examples, name)()
+    low, B, scal = build_case(ocp, method, K, nodes, sizes, seed=1, **kw)
+    eng = make_engine(low, scal)
+    rng = np.random.default_rng(7)
+    for _ in range(2):
+        x = rng.uniform(-0.5, 0.5, low.S.num_x)
+        lam = rng.standard_normal(low.S.num_c)
+        sigma = float(rng.uniform(0.2, 2.0))
+        out = eng.eval_host(ALL, x, lam, sigma)
+        _check(out, B, x, lam, sigma)
+        # single-output variants must agree with the fused launch bit for bit
+        assert np.array_equal(eng.eval_host(E.EVAL_JAC, x)["jac"], out["jac"])
+        assert np.array_equal(eng.eval_host(E.EVAL_HESS, x, lam, sigma)["hess"], out["hess"])
+        assert np.array_equal(eng.eval_host(E.EVAL_C, x)["c"], out["c"])
+        jh = eng.eval_host(E.EVAL_JAC | E.EVAL_HESS, x, lam, sigma)
+        assert np.array_equal(jh["jac"], out["jac"]) and np.array_equal(jh["hess"], out["hess"])
+
+
+def test_golden_brachistochrone_pins(cuda_device):
+    """tests/unit/test_iteration.py:305-385 of the reference, through the CUDA path."""
+    from helpers import GOLDEN
+    ocp = examples.brachistochrone()
+    ocp.initialise()
+    backend = ocp._backend
+    it = backend.mesh_iterations[0]
+    it.generate_nlp()
+    g = np.load(f"{GOLDEN}/iteration_scaling_brachistochrone.npz")
+    x = g["x_tilde"]
+    assert it.num_x == 125 and it.num_c == 90
+    np.testing.assert_almost_equal(backend.evaluate_J(x), 0.8243386694458454)
+    expect_g = np.zeros(125)
+    expect_g[124] = 10
+    np.testing.assert_allclose(backend.evaluate_g(x), expect_g)
+    np.testing.assert_allclose(backend.evaluate_c(x), np.zeros(90), atol=10e-2)
+    rows, cols = backend.evaluate_G_structure()
+    assert backend.evaluate_G_num_nonzero() == len(rows) == len(backend.evaluate_G_nonzeros(x))
+    assert np.all(np.diff(cols) >= 0)                  # CCS: column-major
+
+
+def test_golden_double_pendulum_pins(cuda_device):
+    """tests/unit/test_iteration.py:290-336 of the reference."""
+    from helpers import GOLDEN
+    ocp = examples.double_pendulum()
+    ocp.initialise()
+    backend = ocp._backend
+    it = backend.mesh_iterations[0]
+    it.generate_nlp()
+    g = np.load(f"{GOLDEN}/iteration_scaling_double_pendulum.npz")
+    assert it.num_x == 190 and it.num_c == 121
+    assert backend.evaluate_J(g["x_tilde"]) == 100
+    expect_g = np.zeros(190)
+    expect_g[186] = 1000
+    np.testing.assert_allclose(backend.evaluate_g(g["x_tilde"]), expect_g)
+
+
+def test_batched_instances(cuda_device):
+    ocp = examples.cart_pole_swing_up()
+    low, B, scal = build_case(ocp, "lobatto", 10, 4, seed=3)
+    nb = 16
+    eng = make_engine(low, scal, batch=nb)
+    rng = np.random.default_rng(11)
+    X = rng.uniform(-0.5, 0.5, (nb, low.S.num_x))
+    L = rng.standard_normal((nb, low.S.num_c))
+    sig = rng.uniform(0.5, 1.5, nb)
+    out = eng.eval_host(ALL, X, L, sig)
+    for i in (0, 5, nb - 1):
+        one = {k: v[i:i + 1] for k, v in out.items()}
+        _check(one, B, X[i], L[i], float(sig[i]))
+
+
+def test_device_pointers_and_determinism(cuda_device):
+    import torch
+    ocp = examples.cart_pole_swing_up()
+    low, B, scal = build_case(ocp, "lobatto", 500, 4, seed=5)
+    eng = make_engine(low, scal)
+    S = low.S
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-0.5, 0.5, S.num_x)
+    lam = rng.standard_normal(S.num_c)
+    dx = torch.from_numpy(x).cuda()
+    dl = torch.from_numpy(lam).cuda()
+    jac = torch.full((S.nnz_g,), float("nan"), dtype=torch.float64, device="cuda")
+    hes = torch.full((S.nnz_h,), float("nan"), dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    eng.eval_ptr(E.EVAL_JAC | E.EVAL_HESS, dx, lam=dl, jac=jac, hess=hes, stream=stream)
+    torch.cuda.synchronize()
+    j1, h1 = jac.cpu().numpy().copy(), hes.cpu().numpy().copy()
+    assert max_err(j1, B.G_nonzeros(x)) <= RTOL
+    assert max_err(h1, B.H_nonzeros(x, 1.0, lam)) <= RTOL
+    for _ in range(3):                                    # bitwise reproducible
+        jac.fill_(float("nan"))
+        hes.fill_(float("nan"))
+        eng.eval_ptr(E.EVAL_JAC | E.EVAL_HESS, dx, lam=dl, jac=jac, hess=hes, stream=stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(jac.cpu().numpy(), j1) and np.array_equal(hes.cpu().numpy(), h1)
+
+
+def test_full_size_config2_properties(cuda_device):
+    """BASELINE config 2 (cart-pole, 10^5 nodes): oracle comparison at full size
+    plus size-independent properties (linearity of H in (sigma, lam))."""
+    ocp = examples.cart_pole_swing_up()
+    low, B, scal = build_case(ocp, "lobatto", 33333, 4, seed=9)
+    S = low.S
+    assert (S.num_x, S.num_c, S.nnz_g, S.nnz_h) == (500001, 399997, 3899963, 500000)
+    eng = make_engine(low, scal)
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-0.5, 0.5, S.num_x)
+    lam = rng.standard_normal(S.num_c)
+    out = eng.eval_host(ALL, x, lam, 1.0)
+    _check(out, B, x, lam, 1.0)
+    h2 = eng.eval_host(E.EVAL_HESS, x, 3.0 * lam, 3.0)["hess"][0]
+    assert max_err(h2, 3.0 * out["hess"][0]) <= 1e-13
+    h0 = eng.eval_host(E.EVAL_HESS, x, 0.0 * lam, 0.0)["hess"][0]
+    assert np.all(h0 == 0.0)
