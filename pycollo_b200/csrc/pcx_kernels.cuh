@@ -55,6 +55,13 @@ __device__ __forceinline__ double pcx_block_sum(double v, double* scratch) {
 
 template <int N> struct PcxArr { double v[N > 0 ? N : 1]; };
 
+// x = V * x_tilde + r exactly as the reference composes it (a rounded product,
+// then a rounded sum -- pycollo/backend.py:279-280, scaling.py:176-178): no FMA
+// contraction, so e.g. 1000 * (-0.4) + 500 is exactly 100 as it is in CasADi.
+__device__ __forceinline__ double pcx_unscale(double V, double xt, double r) {
+    return __dadd_rn(__dmul_rn(V, xt), r);
+}
+
 // ---------------------------------------------------------------------------
 // One tile of phase Ph.
 // ---------------------------------------------------------------------------
@@ -159,15 +166,15 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     __syncthreads();
 
     // ---- phase scalars ------------------------------------------------------
-    const double t0 = ps[Ph::OFF_TINFO + 0] * (Ph::HAS_T0 ? x[pb[Ph::PB_T0X]] : 0.0)
-                      + ps[Ph::OFF_TINFO + 1];
-    const double tF = ps[Ph::OFF_TINFO + 2] * (Ph::HAS_TF ? x[pb[Ph::PB_TFX]] : 0.0)
-                      + ps[Ph::OFF_TINFO + 3];
+    const double t0 = pcx_unscale(ps[Ph::OFF_TINFO + 0],
+                                  Ph::HAS_T0 ? x[pb[Ph::PB_T0X]] : 0.0, ps[Ph::OFF_TINFO + 1]);
+    const double tF = pcx_unscale(ps[Ph::OFF_TINFO + 2],
+                                  Ph::HAS_TF ? x[pb[Ph::PB_TFX]] : 0.0, ps[Ph::OFF_TINFO + 3]);
     const double hp = 0.5 * (tF - t0);
     double sv[NS > 0 ? NS : 1];
 #pragma unroll
     for (int j = 0; j < NS; ++j)
-        sv[j] = p.gscal[PCX_GS_VS + j] * x[p.num_x - NS + j] + p.gscal[PCX_GS_RS + j];
+        sv[j] = pcx_unscale(p.gscal[PCX_GS_VS + j], x[p.num_x - NS + j], p.gscal[PCX_GS_RS + j]);
 
     double red[Ph::NRED > 0 ? Ph::NRED : 1];
 #pragma unroll
@@ -195,7 +202,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         double v[NV + NS > 0 ? NV + NS : 1];
 #pragma unroll
         for (int a = 0; a < NV; ++a)
-            v[a] = ps[Ph::OFF_VV + a] * x[xo + (i64)a * N + m] + ps[Ph::OFF_RV + a];
+            v[a] = pcx_unscale(ps[Ph::OFF_VV + a], x[xo + (i64)a * N + m], ps[Ph::OFF_RV + a]);
 #pragma unroll
         for (int j = 0; j < NS; ++j) v[NV + j] = sv[j];
 
@@ -357,10 +364,10 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
                     for (int mm = 0; mm < n_k; ++mm)
                         acc += __dmul_rn(Arow[mm], h_k) * sF[i * nnp + b + mm];
                     if (WANT_C) {
-                        const double ya = ps[Ph::OFF_VV + i] * x[xo + (i64)i * N + node0 + b]
-                                          + ps[Ph::OFF_RV + i];
-                        const double yb = ps[Ph::OFF_VV + i] * x[xo + (i64)i * N + node0 + r + 1]
-                                          + ps[Ph::OFF_RV + i];
+                        const double ya = pcx_unscale(ps[Ph::OFF_VV + i],
+                            x[xo + (i64)i * N + node0 + b], ps[Ph::OFF_RV + i]);
+                        const double yb = pcx_unscale(ps[Ph::OFF_VV + i],
+                            x[xo + (i64)i * N + node0 + r + 1], ps[Ph::OFF_RV + i]);
                         out_c[co + (i64)i * (N - 1) + node0 + r] =
                             ps[Ph::OFF_WFN + i] * ((ya - yb) + hp * acc);
                     }
@@ -457,7 +464,7 @@ __device__ void pcx_border(const PcxParams& p, const int inst, double* scratch)
         bv[0] = 1.0;
         double pt[PCX_NPOINT > 0 ? PCX_NPOINT : 1];
         for (int a = 0; a < PCX_NPOINT; ++a) {
-            pt[a] = p.pt_scal[a] * x[p.pt_x[a]] + p.pt_scal[PCX_NPOINT + a];
+            pt[a] = pcx_unscale(p.pt_scal[a], x[p.pt_x[a]], p.pt_scal[PCX_NPOINT + a]);
             bv[PCX_BV_PTVAL + a] = pt[a];
         }
         double mult[1 + PCX_NB];
@@ -473,10 +480,10 @@ __device__ void pcx_border(const PcxParams& p, const int inst, double* scratch)
             const i64* pb = p.pbase + PCX_PHASE_PBASE(q);
             const double* ps = p.pscal + PCX_PHASE_PSCAL(q);
             const i64 i0 = pb[PCX_PB_T0X], iF = pb[PCX_PB_TFX];
-            const double t0 = ps[PCX_PHASE_TINFO(q) + 0] * (i0 >= 0 ? x[i0] : 0.0)
-                              + ps[PCX_PHASE_TINFO(q) + 1];
-            const double tF = ps[PCX_PHASE_TINFO(q) + 2] * (iF >= 0 ? x[iF] : 0.0)
-                              + ps[PCX_PHASE_TINFO(q) + 3];
+            const double t0 = pcx_unscale(ps[PCX_PHASE_TINFO(q) + 0], i0 >= 0 ? x[i0] : 0.0,
+                                          ps[PCX_PHASE_TINFO(q) + 1]);
+            const double tF = pcx_unscale(ps[PCX_PHASE_TINFO(q) + 2], iF >= 0 ? x[iF] : 0.0,
+                                          ps[PCX_PHASE_TINFO(q) + 3]);
             sRS[1 + q] = 0.5 * (tF - t0);
         }
     }
