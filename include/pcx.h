@@ -73,7 +73,7 @@ typedef struct {
     int32_t bv_size;         /* border value vector length                     */
     int32_t nred_max;        /* max reductions per phase                       */
     int32_t btab_len;        /* quadrature coefficient table length            */
-    int32_t reserved;
+    int32_t reserved;        /* >0: min resident CTAs/SM (__launch_bounds__)    */
     int64_t num_x, num_c, num_dy, nnz_g, nnz_h;
     int64_t smem_bytes;      /* dynamic shared memory per CTA                  */
     const char* problem_header;  /* generated device functions (CUDA C++)     */
@@ -150,6 +150,8 @@ int pcx_host_free(void* ptr);
  * names of the compiled kernel variants (diagnostics for bench.py).          */
 int64_t pcx_launch_count(const pcx_engine* e);
 int     pcx_synchronize(pcx_engine* e, void* stream);
+/* debug: copy the first n doubles of the reduction scratch to the host         */
+int     pcx_debug_read_partials(pcx_engine* e, double* dst, int64_t n);
 
 /* Write `bytes` bytes of scratch on the device (> L2) so the next timed launch
  * starts from a cold L2.                                                     */

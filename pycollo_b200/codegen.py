@@ -175,6 +175,8 @@ def generate(ir, phase_derivs, point_derivs, structure):
         ps_off += lay.pscal_size
         pb_off += lay.pbase_size
         out.append(_phase_struct(q, ph, pd, lay, NS))
+    out.insert(2, f"#define PCX_PSCAL_TOTAL {ps_off}\n#define PCX_PBASE_TOTAL {pb_off}\n"
+                  f"#define PCX_GSCAL_TOTAL {2 * NS + 1 + NB}\n")
     out.append(_gfun("PCX_PHASE_NRED", [l.nred for l in layouts]))
     out.append(_gfun("PCX_PHASE_REDOFF", [t.red_off for t in structure.ph]))
     out.append(_gfun("PCX_PHASE_PBASE", [l.pbase_off for l in layouts]))

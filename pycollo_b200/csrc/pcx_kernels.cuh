@@ -31,6 +31,16 @@
 #ifndef PCX_THREADS
 #define PCX_THREADS 128
 #endif
+#ifndef PCX_MIN_BLOCKS
+#define PCX_MIN_BLOCKS 1
+#endif
+
+// Small per-problem tables live in constant memory (set by the host after the
+// module is loaded and on every pcx_set_scaling): scaling products, slot bases.
+// With compile-time offsets they become direct c[bank][off] operands.
+__constant__ double pcx_c_pscal[PCX_PSCAL_TOTAL > 0 ? PCX_PSCAL_TOTAL : 1];
+__constant__ double pcx_c_gscal[PCX_GSCAL_TOTAL > 0 ? PCX_GSCAL_TOTAL : 1];
+__constant__ long long pcx_c_pbase[PCX_PBASE_TOTAL > 0 ? PCX_PBASE_TOTAL : 1];
 
 __device__ __forceinline__ double pcx_warp_sum(double v) {
 #pragma unroll
@@ -55,6 +65,50 @@ __device__ __forceinline__ double pcx_block_sum(double v, double* scratch) {
 
 template <int N> struct PcxArr { double v[N > 0 ? N : 1]; };
 
+#ifdef PCX_DEBUG_TIMELINE
+// per-CTA phase timestamps (ns) into the partials scratch, 8 slots per tile
+__device__ __forceinline__ void pcx_stamp(const PcxParams& p, int tile, int k) {
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        p.partials[(i64)tile * 8 + k] = (double)(t & ((1ull << 40) - 1));
+    }
+}
+#define PCX_STAMP(k) pcx_stamp(p, tile, k)
+#else
+#define PCX_STAMP(k)
+#endif
+
+// Engine tables (tile/section descriptors, recipes) are re-read by every launch
+// while tens of MB of values stream through L2: load them with an evict_last
+// policy so they stay L2-resident between launches.
+__device__ __forceinline__ unsigned long long pcx_policy_keep() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ long long pcx_ld_keep(const long long* ptr, unsigned long long pol) {
+    long long v;
+    asm volatile("ld.global.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ unsigned long long pcx_ld_keep(const unsigned long long* ptr,
+                                                          unsigned long long pol) {
+    unsigned long long v;
+    asm volatile("ld.global.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double pcx_ld_keep(const double* ptr, unsigned long long pol) {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int pcx_ld_keep(const int* ptr, unsigned long long pol) {
+    int v;
+    asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+
 // x = V * x_tilde + r exactly as the reference composes it (a rounded product,
 // then a rounded sum -- pycollo/backend.py:279-280, scaling.py:176-178): no FMA
 // contraction, so e.g. 1000 * (-0.4) + 500 is exactly 100 as it is in CasADi.
@@ -62,11 +116,22 @@ __device__ __forceinline__ double pcx_unscale(double V, double xt, double r) {
     return __dadd_rn(__dmul_rn(V, xt), r);
 }
 
+// Does this (phase, output selection) accumulate any cross-tile reduction?
+template <class Ph>
+__host__ __device__ constexpr bool pcx_need_red() {
+    return (((PCX_FLAGS & PCX_F_C) != 0) && Ph::NQ > 0)
+        || (((PCX_FLAGS & PCX_F_G) != 0) && (Ph::HAS_T0 || Ph::HAS_TF) && Ph::NQ > 0)
+        || (((PCX_FLAGS & PCX_F_G) != 0) && (Ph::RED_HTS - Ph::RED_GS) > 0)
+        || (((PCX_FLAGS & PCX_F_H) != 0) && (Ph::NHTS > 0 || Ph::NH2SS > 0));
+}
+
 // ---------------------------------------------------------------------------
-// One tile of phase Ph.
+// One tile of phase Ph.  Returns true when the tile wrote something the border
+// pass reads (reduction partials, end-node values) or that it overwrites
+// (gradient zeros), i.e. when its writes must be fenced before the ticket.
 // ---------------------------------------------------------------------------
 template <class Ph>
-__device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
+__device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
                          unsigned char* smem_raw)
 {
     constexpr int F = PCX_FLAGS;
@@ -84,16 +149,22 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     constexpr bool NEED_ROWS = NEED_SF || (WANT_G && NDS > 0);
 
     const int tid = threadIdx.x;
-    const i64* pb = p.pbase + Ph::PBASE_OFF;
-    const double* ps = p.pscal + Ph::PSCAL_OFF;
+    PCX_STAMP(0);
+    const i64* pb = pcx_c_pbase + Ph::PBASE_OFF;
+    const double* ps = pcx_c_pscal + Ph::PSCAL_OFF;
     const i64 N = pb[Ph::PB_N], K = pb[Ph::PB_K];
     const i64 xo = pb[Ph::PB_XOFF], co = pb[Ph::PB_COFF];
     const i64 sec_off = pb[Ph::PB_SECOFF];         // offset into sec_order/h/type
     const i64* sec_node = p.sec_node + sec_off + Ph::INDEX;   // K+1 per phase
-    const int k0 = p.tile_k0[tile], k1 = p.tile_k1[tile];
+    const unsigned long long keep = pcx_policy_keep();
+    const i64* td = p.tile_desc + (i64)tile * 8;   // phase,k0,k1,node0,nn,run0,run1,prev_rows
+    const int k0 = (int)pcx_ld_keep(td + 1, keep), k1 = (int)pcx_ld_keep(td + 2, keep);
     const int nsec = k1 - k0;
-    const i64 node0 = sec_node[k0];
-    const int nn = (int)(sec_node[k1] - node0) + 1;
+    const i64 node0 = pcx_ld_keep(td + 3, keep);
+    const int nn = (int)pcx_ld_keep(td + 4, keep);
+    const int run0 = (int)pcx_ld_keep(td + 5, keep);
+    const int nruns = (int)pcx_ld_keep(td + 6, keep) - run0;
+    const int prev_rows = (int)pcx_ld_keep(td + 7, keep);   // defect rows of section k0-1
     const bool last_tile = (k1 == (int)K);
     const bool has_prev = (k0 > 0);
     const int nnp = nn | 1;                        // odd stride: no bank conflicts
@@ -112,19 +183,35 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     double* sRed = sLam + (WANT_H ? NY * lam_stride : 0);      // T/32
     int* sSecNode = reinterpret_cast<int*>(sRed + T / 32);     // nsec+2 (prev first)
     int* sSecOrder = sSecNode + (nsec + 2);                    // nsec+1 (prev first)
-    int* sSecType = sSecOrder + (nsec + 1);                    // nsec
-    int* sNodeSec = sSecType + nsec;                           // nn
-    int* sStart = sNodeSec + nn;                               // NV * (nsec+1)
-    int* sRecBase = sStart + NV * (nsec + 1);                  // NV * nsec
+    int* sNodeSec = sSecOrder + (nsec + 1);                    // nn
+    __shared__ double sCst[1 + 2 * (NY > 0 ? NY : 1)];
 
-    for (int i = tid; i < p.btab_len; i += T) sB[i] = p.btab[i];
+    // everything below depends only on the tile descriptor: all global loads of
+    // the prologue (this thread's node variables, quadrature table, section
+    // table, multipliers) are in flight together before the first barrier
+    double xt0[NV > 0 ? NV : 1];
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+        xt0[a] = (tid < nn) ? x[xo + (i64)a * N + node0 + tid] : 0.0;
+    const double xt_t0 = Ph::HAS_T0 ? x[pb[Ph::PB_T0X]] : 0.0;
+    const double xt_tF = Ph::HAS_TF ? x[pb[Ph::PB_TFX]] : 0.0;
+    for (int i = tid; i < p.btab_len; i += T) sB[i] = pcx_ld_keep(p.btab + i, keep);
+    if (WANT_G && tid < 1 + 2 * NY) sCst[tid] = ps[Ph::OFF_GCST + tid];
+    if (WANT_H) {
+        // multipliers of the defect rows of sections k0-1 .. k1-1
+        const int nrows = nn - 1 + prev_rows;
+        const i64 row0 = node0 - prev_rows;
+#pragma unroll
+        for (int i = 0; i < NY; ++i)
+            for (int r = tid; r < nrows; r += T)
+                sLam[i * lam_stride + r] = lam[co + (i64)i * (N - 1) + row0 + r];
+    }
     for (int s = tid; s <= nsec; s += T) {
         const int k = k0 - 1 + s;                  // s = 0 is the previous section
         const bool ok = (k >= 0);
-        sHk[s] = ok ? p.sec_h[sec_off + k] : 0.0;
-        sSecOrder[s] = ok ? p.sec_order[sec_off + k] : 0;
-        sSecNode[s] = ok ? (int)(sec_node[k] - node0) : 0;
-        if (s > 0) sSecType[s - 1] = p.sec_type[sec_off + k];
+        sHk[s] = ok ? pcx_ld_keep(p.sec_h + sec_off + k, keep) : 0.0;
+        sSecOrder[s] = ok ? pcx_ld_keep(p.sec_order + sec_off + k, keep) : 0;
+        sSecNode[s] = ok ? (int)(pcx_ld_keep(sec_node + k, keep) - node0) : 0;
     }
     if (tid == 0) sSecNode[nsec + 1] = nn - 1;
     __syncthreads();
@@ -133,48 +220,17 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         for (int m = 0; m < n - 1; ++m) sNodeSec[b + m] = s;
         if (s == nsec - 1) sNodeSec[b + n - 1] = s;
     }
-    if (WANT_G) {
-        const bool uni = p.tile_uniform[tile] != 0;
-        const i64* gp = p.gsec_ptr + pb[Ph::PB_GSECOFF];
-        for (int i = tid; i < NV * (nsec + 1); i += T) {
-            const int a = i / (nsec + 1), s = i - a * (nsec + 1);
-            int v;
-            if (uni) {
-                const int ty = p.sec_type[sec_off + k0];
-                const int* tv = p.type_var_off + ty * (p.nvmax + 1);
-                v = s * (tv[a + 1] - tv[a]);
-            } else {
-                v = (int)(gp[a * (K + 1) + k0 + s] - gp[a * (K + 1) + k0]);
-            }
-            sStart[i] = v;
-        }
-        for (int i = tid; i < NV * nsec; i += T) {
-            const int a = i / nsec, s = i - a * nsec;
-            sRecBase[i] = p.type_var_off[p.sec_type[sec_off + k0 + s] * (p.nvmax + 1) + a];
-        }
-    }
-    if (WANT_H) {
-        // multipliers of the defect rows of sections k0-1 .. k1-1
-        const int prev_rows = has_prev ? sSecOrder[0] - 1 : 0;
-        const int nrows = nn - 1 + prev_rows;
-        const i64 row0 = node0 - prev_rows;
-        for (int i = tid; i < NY * nrows; i += T) {
-            const int st = i / nrows, r = i - st * nrows;
-            sLam[st * lam_stride + r] = lam[co + (i64)st * (N - 1) + row0 + r];
-        }
-    }
     __syncthreads();
+    PCX_STAMP(1);
 
     // ---- phase scalars ------------------------------------------------------
-    const double t0 = pcx_unscale(ps[Ph::OFF_TINFO + 0],
-                                  Ph::HAS_T0 ? x[pb[Ph::PB_T0X]] : 0.0, ps[Ph::OFF_TINFO + 1]);
-    const double tF = pcx_unscale(ps[Ph::OFF_TINFO + 2],
-                                  Ph::HAS_TF ? x[pb[Ph::PB_TFX]] : 0.0, ps[Ph::OFF_TINFO + 3]);
+    const double t0 = pcx_unscale(ps[Ph::OFF_TINFO + 0], xt_t0, ps[Ph::OFF_TINFO + 1]);
+    const double tF = pcx_unscale(ps[Ph::OFF_TINFO + 2], xt_tF, ps[Ph::OFF_TINFO + 3]);
     const double hp = 0.5 * (tF - t0);
     double sv[NS > 0 ? NS : 1];
 #pragma unroll
     for (int j = 0; j < NS; ++j)
-        sv[j] = pcx_unscale(p.gscal[PCX_GS_VS + j], x[p.num_x - NS + j], p.gscal[PCX_GS_RS + j]);
+        sv[j] = pcx_unscale(pcx_c_gscal[PCX_GS_VS + j], x[p.num_x - NS + j], pcx_c_gscal[PCX_GS_RS + j]);
 
     double red[Ph::NRED > 0 ? Ph::NRED : 1];
 #pragma unroll
@@ -202,7 +258,8 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         double v[NV + NS > 0 ? NV + NS : 1];
 #pragma unroll
         for (int a = 0; a < NV; ++a)
-            v[a] = pcx_unscale(ps[Ph::OFF_VV + a], x[xo + (i64)a * N + m], ps[Ph::OFF_RV + a]);
+            v[a] = pcx_unscale(ps[Ph::OFF_VV + a],
+                               ml == tid ? xt0[a] : x[xo + (i64)a * N + m], ps[Ph::OFF_RV + a]);
 #pragma unroll
         for (int j = 0; j < NS; ++j) v[NV + j] = sv[j];
 
@@ -218,24 +275,30 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
 #pragma unroll
         for (int e = 0; e < NF; ++e) { muh[e] = 0.0; mut[e] = 0.0; }
         if (WANT_H) {
-            const int prev_rows = has_prev ? sSecOrder[0] - 1 : 0;
+            double lacc[NY > 0 ? NY : 1];
+#pragma unroll
+            for (int i = 0; i < NY; ++i) lacc[i] = 0.0;
+            if (start_with_prev) {
+                const double* Apr = sB + p.order_a_off[n_pr] + n_pr - 1;
+                const double* lrow = sLam + prev_rows + sSecNode[s];
+                for (int l = 0; l < n_pr - 1; ++l) {
+                    const double cl = __dmul_rn(Apr[l * n_pr], h_pr);
+#pragma unroll
+                    for (int i = 0; i < NY; ++i) lacc[i] += lrow[i * lam_stride + l] * cl;
+                }
+            }
+            if (owned) {
+                const double* Ak = sB + p.order_a_off[n_k] + mloc;
+                const double* lrow = sLam + prev_rows + sSecNode[s + 1];
+                for (int l = 0; l < n_k - 1; ++l) {
+                    const double cl = __dmul_rn(Ak[l * n_k], h_k);
+#pragma unroll
+                    for (int i = 0; i < NY; ++i) lacc[i] += lrow[i * lam_stride + l] * cl;
+                }
+            }
 #pragma unroll
             for (int i = 0; i < NY; ++i) {
-                double acc = 0.0;
-                const double* lrow = sLam + i * lam_stride + prev_rows;
-                if (start_with_prev) {
-                    const double* Apr = sB + p.order_a_off[n_pr];
-                    const int rb = sSecNode[s];         // first row of prev section
-                    for (int l = 0; l < n_pr - 1; ++l)
-                        acc += lrow[rb + l] * __dmul_rn(Apr[l * n_pr + n_pr - 1], h_pr);
-                }
-                if (owned) {
-                    const double* Ak = sB + p.order_a_off[n_k];
-                    const int rb = sSecNode[s + 1];
-                    for (int l = 0; l < n_k - 1; ++l)
-                        acc += lrow[rb + l] * __dmul_rn(Ak[l * n_k + mloc], h_k);
-                }
-                const double mu = ps[Ph::OFF_WFN + i] * acc;
+                const double mu = ps[Ph::OFF_WFN + i] * lacc[i];
                 mut[i] = mu;
                 muh[i] = hp * mu;
             }
@@ -346,6 +409,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     }
     __syncthreads();
 
+    PCX_STAMP(2);
     // ---- row-oriented contractions: defect rows of c, t/s columns of G -------
     if (NEED_ROWS) {
         for (int r = tid; r < nn - 1; r += T) {
@@ -393,38 +457,76 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         }
     }
 
-    // ---- coalesced scatter of the Jacobian values, one variable at a time ----
+    // ---- coalesced scatter of the Jacobian values ------------------------------
+    // A section of a given type owns, for every variable a, a fixed "period" of
+    // P_a value slots; the host lists the tile as runs of consecutive same-type
+    // sections (one run per tile on a uniform mesh, plus a one-section run in the
+    // first and last tile).  Thread t takes ONE slot u of the concatenated period
+    // (all variables): its 64-bit recipe word is decoded once per run and the
+    // loop over the run's sections is  3 x LDS, DMUL, DFMA, STG + pointer bumps.
+    // Consecutive threads write consecutive addresses inside a variable's period,
+    // and a variable's periods of consecutive sections are back to back.
     if (WANT_G) {
+        const double* cst = sCst;
+        const int nvp1 = p.nvmax + 1;
 #pragma unroll 1
-        for (int a = 0; a < NV; ++a) {
-            const int* st = sStart + a * (nsec + 1);
-            const int len = st[nsec];
-            if (len == 0) continue;
-            const i64 base = p.tile_gbase[(i64)tile * p.nvmax + a];
-            const float inv = (float)nsec / (float)len;
-            const double* cst = ps + Ph::OFF_GCST;
-            for (int idx = tid; idx < len; idx += T) {
-                int s = min(nsec - 1, (int)((float)idx * inv));
-                while (idx < st[s]) --s;
-                while (idx >= st[s + 1]) ++s;
-                const int local = idx - st[s];
-                const u32 w = __ldg(p.recipes + sRecBase[a * nsec + s] + local);
-                if (w >> RC_SKIP_BIT) continue;
-                const int e = w & ((1u << RC_E_BITS) - 1);
-                const int bi = (w >> RC_B_SHIFT) & ((1u << RC_B_BITS) - 1);
-                const int ml = sSecNode[s + 1] + (int)((w >> RC_M_SHIFT) & ((1u << RC_M_BITS) - 1));
-                const int ci = (w >> RC_C_SHIFT) & ((1u << RC_C_BITS) - 1);
-                const bool prev = (w >> RC_PREV_BIT) & 1u;
-                const bool plain = (w >> RC_PLAIN_BIT) & 1u;
-                const double d = e ? sD[(e - 1) * nnp + ml] : 0.0;
-                const double coef = plain ? 1.0 : __dmul_rn(sB[bi], prev ? sHk[s] : sHk[s + 1]);
-                out_g[base + idx] = coef * d + cst[ci];
+        for (int r = 0; r < nruns; ++r) {
+            const int s_lo = pcx_ld_keep(p.run_slo + run0 + r, keep);
+            const int s_hi = pcx_ld_keep(p.run_shi + run0 + r, keep);
+            const int* tv = p.type_var_off + pcx_ld_keep(p.run_type + run0 + r, keep) * nvp1;
+            const int rec0 = tv[0];
+            const int Ptot = tv[NV] - rec0;                  // slots per section, all variables
+            if (Ptot == 0) continue;
+            int per = 1, u0 = tid, sc0 = s_lo;
+            if (Ptot < T) {                                  // several sections per pass
+                per = T / Ptot;
+                const int q = tid / Ptot;
+                u0 = tid - q * Ptot;
+                sc0 = s_lo + q;
+                if (q >= per) continue;
+            }
+            for (int u = u0; u < Ptot; u += T) {
+                const unsigned long long w = pcx_ld_keep(p.recipes + rec0 + u, keep);
+                const u32 lo = (u32)w;
+                if (!(lo >> RC_SKIP_BIT)) {
+                    const int a = (int)((w >> 32) & 0xffu);
+                    const int local = (int)(w >> 40);
+                    const int Pa = tv[a + 1] - tv[a];
+                    const int e = lo & ((1u << RC_E_BITS) - 1);
+                    const int bi = (lo >> RC_B_SHIFT) & ((1u << RC_B_BITS) - 1);
+                    const int mloc = (lo >> RC_M_SHIFT) & ((1u << RC_M_BITS) - 1);
+                    const double cc = cst[(lo >> RC_C_SHIFT) & ((1u << RC_C_BITS) - 1)];
+                    const int hsel = ((lo >> RC_PREV_BIT) & 1u) ? 0 : 1;
+                    const bool plain = (lo >> RC_PLAIN_BIT) & 1u;
+                    const double bcoef = sB[bi];
+                    const double* drow = sD + (e ? (e - 1) * nnp : 0) + mloc;
+                    double* o = out_g + pcx_ld_keep(p.run_gbase + (i64)(run0 + r) * p.nvmax + a, keep) + local
+                                + (i64)(sc0 - s_lo) * Pa;
+                    const int ostep = per * Pa;
+                    const int* nd = sSecNode + 1;
+                    const double* hk = sHk + hsel;
+                    int off = 0;
+                    if (e == 0) {
+#pragma unroll 4
+                        for (int sc = sc0; sc < s_hi; sc += per, off += ostep) o[off] = cc;
+                    } else if (plain) {
+#pragma unroll 4
+                        for (int sc = sc0; sc < s_hi; sc += per, off += ostep)
+                            o[off] = drow[nd[sc]];
+                    } else {
+#pragma unroll 4
+                        for (int sc = sc0; sc < s_hi; sc += per, off += ostep)
+                            o[off] = __dmul_rn(bcoef, hk[sc]) * drow[nd[sc]] + cc;
+                    }
+                }
+                if (Ptot < T) break;
             }
         }
     }
 
+    PCX_STAMP(3);
     // ---- reductions -> per-tile partials ---------------------------------------
-    if (Ph::NRED > 0) {
+    if (pcx_need_red<Ph>()) {
 #pragma unroll
         for (int k = 0; k < Ph::NRED; ++k) {
             const double r = pcx_block_sum(red[k], sRed);
@@ -432,6 +534,8 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
                 p.partials[((i64)inst * p.num_tiles + tile) * p.nred_max + k] = r;
         }
     }
+    return pcx_need_red<Ph>() || (WANT_H && (k0 == 0 || last_tile))
+           || (WANT_GRAD && (k0 == 0 || last_tile || tile == 0));
 }
 
 // ---------------------------------------------------------------------------
@@ -448,8 +552,12 @@ __device__ void pcx_border(const PcxParams& p, const int inst, double* scratch)
 
     // 1. final reductions: deterministic (fixed stride, fixed shuffle tree)
     for (int q = 0; q < PCX_NUM_PHASES; ++q) {
-        const int nred = PCX_PHASE_NRED(q);
-        const i64* pbq = p.pbase + PCX_PHASE_PBASE(q);
+        bool need = false;
+#define PCX_CASE(P) if (q == P) need = pcx_need_red<PcxPhase<P> >();
+        PCX_FOREACH_PHASE(PCX_CASE)
+#undef PCX_CASE
+        const int nred = need ? PCX_PHASE_NRED(q) : 0;
+        const i64* pbq = pcx_c_pbase + PCX_PHASE_PBASE(q);
         const int t_lo = (int)pbq[PCX_PB_TILE0], t_hi = (int)pbq[PCX_PB_TILE1];
         for (int k = 0; k < nred; ++k) {
             double acc = 0.0;
@@ -459,39 +567,59 @@ __device__ void pcx_border(const PcxParams& p, const int inst, double* scratch)
             if (tid == 0) bv[PCX_PHASE_REDOFF(q) + k] = r;
         }
     }
-    // 2. point functions and runtime scalars
-    if (tid == 0) {
-        bv[0] = 1.0;
-        double pt[PCX_NPOINT > 0 ? PCX_NPOINT : 1];
-        for (int a = 0; a < PCX_NPOINT; ++a) {
-            pt[a] = pcx_unscale(p.pt_scal[a], x[p.pt_x[a]], p.pt_scal[PCX_NPOINT + a]);
-            bv[PCX_BV_PTVAL + a] = pt[a];
-        }
-        double mult[1 + PCX_NB];
-        const double sg = (p.sigma != nullptr) ? p.sigma[inst] : 1.0;
-        mult[0] = sg * p.gscal[PCX_GS_W];
-        for (int k = 0; k < PCX_NB; ++k)
-            mult[1 + k] = (F & PCX_F_H)
-                ? p.lam[(i64)inst * p.num_c + (p.num_c - PCX_NB) + k] * p.gscal[PCX_GS_WB + k]
+    // 2. point variables, multipliers and runtime scalars: one thread each, so
+    //    the dependent global loads overlap instead of queueing on thread 0
+    __shared__ double sPt[PCX_NPOINT > 0 ? PCX_NPOINT : 1];
+    __shared__ double sMult[1 + PCX_NB];
+    for (int a = tid; a < PCX_NPOINT; a += T) {
+        const double v = pcx_unscale(p.pt_scal[a], x[p.pt_x[a]], p.pt_scal[PCX_NPOINT + a]);
+        sPt[a] = v;
+        bv[PCX_BV_PTVAL + a] = v;
+    }
+    for (int k = tid; k <= PCX_NB; k += T) {
+        if (k == 0) {
+            const double sg = (p.sigma != nullptr) ? p.sigma[inst] : 1.0;
+            sMult[0] = sg * pcx_c_gscal[PCX_GS_W];
+        } else {
+            sMult[k] = (F & PCX_F_H)
+                ? p.lam[(i64)inst * p.num_c + (p.num_c - PCX_NB) + (k - 1)]
+                  * pcx_c_gscal[PCX_GS_WB + (k - 1)]
                 : 0.0;
-        pcx_point_eval(pt, mult, bv + PCX_BV_PTFN, bv + PCX_BV_PTD1, bv + PCX_BV_PTD2);
-        sRS[0] = 1.0;
-        for (int q = 0; q < PCX_NUM_PHASES; ++q) {
-            const i64* pb = p.pbase + PCX_PHASE_PBASE(q);
-            const double* ps = p.pscal + PCX_PHASE_PSCAL(q);
-            const i64 i0 = pb[PCX_PB_T0X], iF = pb[PCX_PB_TFX];
-            const double t0 = pcx_unscale(ps[PCX_PHASE_TINFO(q) + 0], i0 >= 0 ? x[i0] : 0.0,
-                                          ps[PCX_PHASE_TINFO(q) + 1]);
-            const double tF = pcx_unscale(ps[PCX_PHASE_TINFO(q) + 2], iF >= 0 ? x[iF] : 0.0,
-                                          ps[PCX_PHASE_TINFO(q) + 3]);
-            sRS[1 + q] = 0.5 * (tF - t0);
         }
     }
+    for (int q = tid; q <= PCX_NUM_PHASES; q += T) {
+        if (q == 0) { sRS[0] = 1.0; bv[0] = 1.0; continue; }
+        const int qq = q - 1;
+        const i64* pb = pcx_c_pbase + PCX_PHASE_PBASE(qq);
+        const double* ps = pcx_c_pscal + PCX_PHASE_PSCAL(qq);
+        const i64 i0 = pb[PCX_PB_T0X], iF = pb[PCX_PB_TFX];
+        const double t0 = pcx_unscale(ps[PCX_PHASE_TINFO(qq) + 0], i0 >= 0 ? x[i0] : 0.0,
+                                      ps[PCX_PHASE_TINFO(qq) + 1]);
+        const double tF = pcx_unscale(ps[PCX_PHASE_TINFO(qq) + 2], iF >= 0 ? x[iF] : 0.0,
+                                      ps[PCX_PHASE_TINFO(qq) + 3]);
+        sRS[q] = 0.5 * (tF - t0);
+    }
+    // prefetch this thread's border-map entries while the point function runs
+    int e_grp = -1, e_k0 = 0, e_k1 = 0;
+    i64 e_slot = 0;
+    if (tid < p.n_border) {
+        e_grp = p.border_grp[tid];
+        e_slot = p.border_slot[tid];
+        e_k0 = p.border_ptr[tid];
+        e_k1 = p.border_ptr[tid + 1];
+    }
     __syncthreads();
-    __threadfence();
+    if (tid == 0)
+        pcx_point_eval(sPt, sMult, bv + PCX_BV_PTFN, bv + PCX_BV_PTD1, bv + PCX_BV_PTD2);
+    __syncthreads();
     // 3. the border map
     for (int e = tid; e < p.n_border; e += T) {
-        const int grp = p.border_grp[e];
+        int grp = e_grp, k0 = e_k0, k1 = e_k1;
+        i64 slot = e_slot;
+        if (e != tid) {
+            grp = p.border_grp[e]; slot = p.border_slot[e];
+            k0 = p.border_ptr[e]; k1 = p.border_ptr[e + 1];
+        }
         double* out;
         if (grp == 0) { if (!(F & PCX_F_C)) continue; out = p.c + (i64)inst * p.num_c; }
         else if (grp == 1) { if (!(F & PCX_F_G)) continue; out = p.gj + (i64)inst * p.nnz_g; }
@@ -499,28 +627,35 @@ __device__ void pcx_border(const PcxParams& p, const int inst, double* scratch)
         else if (grp == 3) { if (!(F & PCX_F_J)) continue; out = p.jval + inst; }
         else { if (!(F & PCX_F_GRAD)) continue; out = p.grad + (i64)inst * p.num_x; }
         double acc = 0.0;
-        for (int k = p.border_ptr[e]; k < p.border_ptr[e + 1]; ++k)
+        for (int k = k0; k < k1; ++k)
             acc += p.border_coef[k] * bv[p.border_bv[k]] * sRS[p.border_rs[k]];
-        out[p.border_slot[e]] = acc;
+        out[slot] = acc;
     }
 }
 
-extern "C" __global__ void __launch_bounds__(PCX_THREADS)
+extern "C" __global__ void __launch_bounds__(PCX_THREADS, PCX_MIN_BLOCKS)
 PCX_KERNEL_NAME(const PcxParams p)
 {
     extern __shared__ __align__(16) unsigned char pcx_smem[];
     __shared__ int sLast;
     const int tile = blockIdx.x, inst = blockIdx.y;
-    const int phase = p.tile_phase[tile];
+    const int phase = (int)p.tile_desc[(long long)tile * 8];
+    bool fence = false;
     switch (phase) {
-#define PCX_CASE(P) case P: pcx_tile<PcxPhase<P> >(p, tile, inst, pcx_smem); break;
+#define PCX_CASE(P) case P: fence = pcx_tile<PcxPhase<P> >(p, tile, inst, pcx_smem); break;
         PCX_FOREACH_PHASE(PCX_CASE)
 #undef PCX_CASE
         default: break;
     }
-    // ticket: the last CTA of this instance runs the border pass
-    __threadfence();
+#ifdef PCX_DEBUG_NO_TICKET
+    return;
+#endif
+    // ticket: the last CTA of this instance runs the border pass.  Only tiles
+    // whose writes the border pass depends on pay for a fence (it waits for all
+    // of the CTA's stores to drain); the bulk value stores need no ordering.
+    if (fence) __threadfence();
     __syncthreads();
+    PCX_STAMP(4);
     if (threadIdx.x == 0) {
         const u32 t = atomicAdd(p.ticket + inst, 1u);
         sLast = (t == (u32)p.num_tiles - 1u);
@@ -528,7 +663,11 @@ PCX_KERNEL_NAME(const PcxParams p)
     __syncthreads();
     if (sLast) {
         __threadfence();
+#ifndef PCX_DEBUG_NO_BORDER
         pcx_border(p, inst, reinterpret_cast<double*>(pcx_smem));
+#endif
         if (threadIdx.x == 0) p.ticket[inst] = 0u;
+        PCX_STAMP(6);
     }
+    PCX_STAMP(5);
 }

@@ -39,14 +39,14 @@ struct PcxParams {
     i64 num_x, num_c, num_dy, nnz_g, nnz_h;
     int num_tiles, batch, nvmax, n_border, bv_size, nred_max, btab_len, pad0;
     // tiles
-    const int* tile_phase; const int* tile_k0; const int* tile_k1;
-    const int* tile_uniform; const i64* tile_gbase;
+    const i64* tile_desc;   // 8 per tile: phase,k0,k1,node0,nn,run0,run1,-
+    const int* run_slo; const int* run_shi; const int* run_type;
+    const i64* run_gbase;   // nvmax per run: slot of the run's first period
     // sections (all phases concatenated; sec_node has K+1 entries per phase)
     const i64* sec_node; const int* sec_order; const double* sec_h;
     const int* sec_type;
-    const i64* gsec_ptr;    // per phase NV*(K+1)
     // recipes
-    const u32* recipes; const int* type_var_off;
+    const unsigned long long* recipes; const int* type_var_off;
     const double* btab; const int* order_a_off; const int* order_w_off;
     // scaling-dependent tables (rewritten by pcx_set_scaling)
     const double* pscal; const double* gscal;

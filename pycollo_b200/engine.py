@@ -90,10 +90,10 @@ def load_library(rebuild=False):
 
 
 _TABLE_DTYPES = {
-    "tile_phase": np.int32, "tile_k0": np.int32, "tile_k1": np.int32,
-    "tile_uniform": np.int32, "tile_gbase": np.int64, "sec_node": np.int64,
+    "tile_desc": np.int64, "run_slo": np.int32, "run_shi": np.int32,
+    "run_type": np.int32, "run_gbase": np.int64, "sec_node": np.int64,
     "sec_order": np.int32, "sec_h": np.float64, "sec_type": np.int32,
-    "gsec_ptr": np.int64, "recipes": np.uint32, "type_var_off": np.int32,
+    "recipes": np.uint64, "type_var_off": np.int32,
     "btab": np.float64, "order_a_off": np.int32, "order_w_off": np.int32,
     "pbase": np.int64, "border_grp": np.int32, "border_slot": np.int64,
     "border_ptr": np.int32, "border_bv": np.int32, "border_rs": np.int32,
@@ -104,14 +104,13 @@ _TABLE_DTYPES = {
 def build_tables(S, layouts):
     """All integer / quadrature tables of one (problem, mesh) for pcx_create."""
     t = {}
-    t["tile_phase"], t["tile_k0"], t["tile_k1"] = S.tile_phase, S.tile_k0, S.tile_k1
-    t["tile_uniform"] = S.tile_uniform
-    t["tile_gbase"] = S.tile_gbase.ravel()
+    t["tile_desc"] = S.tile_desc.ravel()
+    t["run_slo"], t["run_shi"], t["run_type"] = S.run_slo, S.run_shi, S.run_type
+    t["run_gbase"] = S.run_gbase.ravel()
     t["sec_node"] = np.concatenate([ph.sec_node for ph in S.ph])
     t["sec_order"] = np.concatenate([ph.sec_order for ph in S.ph])
     t["sec_h"] = np.concatenate([ph.sec_h for ph in S.ph])
     t["sec_type"] = np.concatenate([ph.sec_type for ph in S.ph])
-    t["gsec_ptr"] = np.concatenate([ph.gsec_ptr.ravel() for ph in S.ph])
     t["recipes"] = S.recipe_words
     t["type_var_off"] = S.type_var_off.ravel()
     t["btab"] = S.btab
@@ -212,7 +211,7 @@ def smem_bytes(S, layouts, threads):
         nds = sum(1 for e, _ in pd.d1s if pd.fam[e] == "d")
         dbl = (len(S.btab) + SS + 1 + (pd.NY + len(pd.d1v) + nds) * (NN | 1)
                + pd.NY * (NN + 16) + threads // 32 + 2)
-        ints = (SS + 2) + (SS + 1) + SS + NN + pd.NV * (SS + 1) + pd.NV * SS + 4
+        ints = (SS + 2) + (SS + 1) + NN + 8
         best = max(best, 8 * dbl + 4 * ints)
     return int((best + 15) // 16 * 16)
 
@@ -230,7 +229,7 @@ def _ptr(a):
 class Engine:
     """One compiled problem on one mesh on one device (wraps ``pcx_engine``)."""
 
-    def __init__(self, S, layouts, header, *, batch=1, device=0):
+    def __init__(self, S, layouts, header, *, batch=1, device=0, min_blocks=None):
         self.lib = load_library()
         self.S, self.layouts = S, layouts
         self.batch = int(batch)
@@ -254,7 +253,8 @@ class Engine:
                      num_tiles=S.num_tiles, nvmax=S.NVMAX,
                      n_border=len(S.border_grp), bv_size=S.bv_size,
                      nred_max=max([l.nred for l in layouts] + [1]),
-                     btab_len=len(S.btab), reserved=0,
+                     btab_len=len(S.btab),
+                     reserved=self._min_blocks(min_blocks, S),
                      num_x=S.num_x, num_c=S.num_c, num_dy=S.num_dy,
                      nnz_g=S.nnz_g, nnz_h=S.nnz_h, smem_bytes=self.smem,
                      problem_header=self._header, num_tables=n, tables=arr)
@@ -264,6 +264,18 @@ class Engine:
             raise PcxError(f"pcx_create failed ({rc}): "
                            f"{self.lib.pcx_last_error(None).decode(errors='replace')}")
         self.h = h
+
+    @staticmethod
+    def _min_blocks(min_blocks, S):
+        """CTAs to keep resident per SM: one full wave on large meshes."""
+        if min_blocks is None and "PCX_MIN_BLOCKS" in os.environ:
+            min_blocks = int(os.environ["PCX_MIN_BLOCKS"])
+        if min_blocks is None:
+            from .structure import RESIDENT_CTAS
+            per_sm = -(-S.num_tiles * 1 // 148)
+            min_blocks = max(1, min(RESIDENT_CTAS, per_sm)) if S.threads <= 128 else \
+                max(1, min(3, per_sm))
+        return int(min_blocks)
 
     def __del__(self):
         h = getattr(self, "h", None)

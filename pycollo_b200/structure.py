@@ -39,6 +39,11 @@ RC_C_SHIFT = RC_M_SHIFT + RC_M_BITS
 RC_PREV_BIT = RC_C_SHIFT + RC_C_BITS          # 29
 RC_PLAIN_BIT = RC_PREV_BIT + 1                # 30
 RC_SKIP_BIT = RC_PLAIN_BIT + 1                # 31
+RC_VAR_SHIFT = 32                             # variable index (8 bits)
+RC_LOCAL_SHIFT = 40                           # slot inside the variable's period
+
+# CTAs the kernels are compiled to keep resident per SM on large meshes
+RESIDENT_CTAS = 6
 
 # border-map groups
 GRP_C, GRP_G, GRP_H, GRP_J, GRP_GRAD = 0, 1, 2, 3, 4
@@ -124,7 +129,7 @@ class PhaseTables:
 class NLPStructure:
     def __init__(self, ir, phase_derivs, point_derivs, meshes, *, prune=True,
                  sm_count=148, threads=128, max_tile_nodes=None,
-                 smem_budget=96 * 1024):
+                 smem_budget=96 * 1024, tiles_per_sm=None):
         self.ir = ir
         self.pd = phase_derivs
         self.pt = point_derivs
@@ -139,7 +144,7 @@ class NLPStructure:
         self._scales_setup()
         self._build_G()
         self._build_H()
-        self._build_tiles(sm_count, max_tile_nodes, smem_budget)
+        self._build_tiles(sm_count, max_tile_nodes, smem_budget, tiles_per_sm)
         self._build_border()
 
     # ------------------------------------------------------------ layout --
@@ -358,11 +363,13 @@ class NLPStructure:
                     if a < NV:
                         for (mloc, rk, idx, l, prev, st, bidx, cidx, plain,
                              skip) in rec[a]:
+                            local = len(words) - offs[-1]
                             words.append(
                                 (st << RC_E_SHIFT) | (bidx << RC_B_SHIFT)
                                 | (mloc << RC_M_SHIFT) | (cidx << RC_C_SHIFT)
                                 | (prev << RC_PREV_BIT) | (plain << RC_PLAIN_BIT)
-                                | (skip << RC_SKIP_BIT))
+                                | (skip << RC_SKIP_BIT)
+                                | (a << RC_VAR_SHIFT) | (local << RC_LOCAL_SHIFT))
                 offs.append(len(words))
                 self.type_var_off.append(offs)
                 t.type_ids.append(len(self.types) - 1)
@@ -477,7 +484,7 @@ class NLPStructure:
             slot = self._g_endpoint_rows(g_rows_parts, g_cols_parts, g_slot_parts,
                                          slot, col)
         self.nnz_g = slot
-        self.recipe_words = np.asarray(words, dtype=np.uint32)
+        self.recipe_words = np.asarray(words, dtype=np.uint64)
         self.type_var_off = np.asarray(self.type_var_off, dtype=np.int32)
         self._g_parts = (g_rows_parts, g_cols_parts, g_slot_parts)
         self._G_rows = self._G_cols = None
@@ -693,7 +700,7 @@ class NLPStructure:
         return 8 * (pd.NY + len(pd.d1v) + 1 + sum(1 for e, _ in pd.d1s
                                                   if pd.fam[e] == "d") + 2)
 
-    def _build_tiles(self, sm_count, max_tile_nodes, smem_budget):
+    def _build_tiles(self, sm_count, max_tile_nodes, smem_budget, tiles_per_sm=None):
         T = self.threads
         tiles = []
         total_nodes = sum(t.N for t in self.ph)
@@ -706,6 +713,10 @@ class NLPStructure:
             if total_nodes >= 32 * sm_count:
                 share = t.N / total_nodes
                 m = max(1, int(np.ceil(want / (sm_count * share))))
+                if tiles_per_sm:
+                    m = max(m, int(tiles_per_sm))
+                elif m > RESIDENT_CTAS:
+                    m = -(-m // RESIDENT_CTAS) * RESIDENT_CTAS   # whole waves
                 want = max(want, int(round(m * sm_count * share)))
             want = min(want, t.K)
             edges = self._balanced_edges(t.sec_node, want, cap)
@@ -715,20 +726,36 @@ class NLPStructure:
         self.tile_k0 = np.array([x[1] for x in tiles], dtype=np.int32)
         self.tile_k1 = np.array([x[2] for x in tiles], dtype=np.int32)
         self.num_tiles = len(tiles)
+        # runs of consecutive same-type sections inside each tile
+        desc = np.zeros((self.num_tiles, 8), dtype=np.int64)
+        run_slo, run_shi, run_type, run_gbase = [], [], [], []
         nn = []
-        uni = []
-        gbase = np.zeros((self.num_tiles, self.NVMAX), dtype=np.int64)
         for it, (ip, k0, k1) in enumerate(tiles):
             t = self.ph[ip]
             nn.append(int(t.sec_node[k1] - t.sec_node[k0] + 1))
             ty = t.sec_type[k0:k1]
-            uni.append(int(np.all(ty == ty[0])))
-            gbase[it, :t.gsec_ptr.shape[0]] = t.gsec_ptr[:, k0]
+            cuts = np.concatenate([[0], np.flatnonzero(ty[1:] != ty[:-1]) + 1,
+                                   [k1 - k0]])
+            prev_rows = int(t.sec_order[k0 - 1]) - 1 if k0 > 0 else 0
+            desc[it] = (ip, k0, k1, t.sec_node[k0], nn[-1], len(run_slo),
+                        len(run_slo) + len(cuts) - 1, prev_rows)
+            NV = t.gsec_ptr.shape[0]
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                run_slo.append(int(lo))
+                run_shi.append(int(hi))
+                run_type.append(int(ty[lo]))
+                gb = np.zeros(self.NVMAX, dtype=np.int64)
+                gb[:NV] = t.gsec_ptr[:, k0 + lo]
+                run_gbase.append(gb)
+        self.tile_desc = desc
+        self.run_slo = np.asarray(run_slo, dtype=np.int32)
+        self.run_shi = np.asarray(run_shi, dtype=np.int32)
+        self.run_type = np.asarray(run_type, dtype=np.int32)
+        self.run_gbase = np.asarray(run_gbase, dtype=np.int64).reshape(-1, self.NVMAX)
         self.tile_nodes = np.asarray(nn, dtype=np.int32)
-        self.tile_uniform = np.asarray(uni, dtype=np.int32)
-        self.tile_gbase = gbase
         self.max_tile_nodes = int(max(nn))
         self.max_tile_secs = int(np.max(self.tile_k1 - self.tile_k0))
+        self.max_tile_runs = int(np.max(desc[:, 6] - desc[:, 5]))
 
     @staticmethod
     def _balanced_edges(sec_node, want, cap):

@@ -85,7 +85,8 @@ def emulate(low, tables, scal, x, lam=None, sigma=1.0, flags=F_G | F_H):
     sB = T["btab"]
     sec_node_all = T["sec_node"]
     for tile in range(S.num_tiles):
-        q = int(T["tile_phase"][tile])
+        td = T["tile_desc"].reshape(-1, 8)[tile]
+        q = int(td[0])
         lay, pd = layouts[q], layouts[q].pd
         fn = _node_fn(pd, NS)
         pb = T["pbase"][lay.pbase_off:lay.pbase_off + lay.pbase_size]
@@ -95,15 +96,17 @@ def emulate(low, tables, scal, x, lam=None, sigma=1.0, flags=F_G | F_H):
         N, K, xo, co = (int(pb[ob[k]]) for k in ("N", "K", "XOFF", "COFF"))
         sec_off = int(pb[ob["SECOFF"]])
         sec_node = sec_node_all[sec_off + q:sec_off + q + K + 1]
-        k0, k1 = int(T["tile_k0"][tile]), int(T["tile_k1"][tile])
+        k0, k1 = int(td[1]), int(td[2])
         nsec = k1 - k0
-        node0 = int(sec_node[k0])
-        nn = int(sec_node[k1]) - node0 + 1
+        node0 = int(td[3])
+        nn = int(td[4])
+        assert node0 == int(sec_node[k0]) and nn == int(sec_node[k1]) - node0 + 1
+        run0, nruns = int(td[5]), int(td[6] - td[5])
         last_tile, has_prev = (k1 == K), (k0 > 0)
         sHk = [T["sec_h"][sec_off + k] if k >= 0 else 0.0 for k in range(k0 - 1, k1)]
         sOrd = [int(T["sec_order"][sec_off + k]) if k >= 0 else 0 for k in range(k0 - 1, k1)]
+        assert int(td[7]) == (sOrd[0] - 1 if has_prev else 0)
         sNode = [int(sec_node[k]) - node0 if k >= 0 else 0 for k in range(k0 - 1, k1)] + [nn - 1]
-        sType = [int(T["sec_type"][sec_off + k]) for k in range(k0, k1)]
         sNodeSec = [0] * nn
         for s in range(nsec):
             b, n = sNode[s + 1], sOrd[s + 1]
@@ -112,16 +115,6 @@ def emulate(low, tables, scal, x, lam=None, sigma=1.0, flags=F_G | F_H):
             if s == nsec - 1:
                 sNodeSec[b + n - 1] = s
         tvo = T["type_var_off"].reshape(-1, NVMAX + 1)
-        gp = T["gsec_ptr"][int(pb[ob["GSECOFF"]]):].reshape(-1)[:NV * (K + 1)].reshape(NV, K + 1)
-        uni = bool(T["tile_uniform"][tile])
-        sStart = np.zeros((NV, nsec + 1), dtype=np.int64)
-        for a in range(NV):
-            for s in range(nsec + 1):
-                if uni:
-                    ty = int(T["sec_type"][sec_off + k0])
-                    sStart[a, s] = s * (tvo[ty, a + 1] - tvo[ty, a])
-                else:
-                    sStart[a, s] = gp[a, k0 + s] - gp[a, k0]
         prev_rows = sOrd[0] - 1 if has_prev else 0
         t0 = ps[o["TINFO"]] * (x[int(pb[ob["T0X"]])] if lay.has_t0 else 0.0) + ps[o["TINFO"] + 1]
         tF = ps[o["TINFO"] + 2] * (x[int(pb[ob["TFX"]])] if lay.has_tF else 0.0) + ps[o["TINFO"] + 3]
@@ -255,30 +248,33 @@ def emulate(low, tables, scal, x, lam=None, sigma=1.0, flags=F_G | F_H):
                         acc = sum((sB[A0 + mm] * h_k) * sDS[kd, b + mm] for mm in range(n_k))
                         out["jac"][int(pb[ob["GSCOL"] + k]) + node0 + r] = acc
                         kd += 1
-        # G scatter
+        # G scatter (runs of same-type sections, flattened 64-bit recipes)
         if flags & F_G:
             cst = ps[o["GCST"]:o["GCST"] + 1 + 2 * NY]
-            for a in range(NV):
-                stt = sStart[a]
-                ln = int(stt[nsec])
-                base = int(T["tile_gbase"][tile * NVMAX + a])
-                for idx in range(ln):
-                    s = int(np.searchsorted(stt, idx, side="right")) - 1
-                    while stt[s + 1] <= idx:
-                        s += 1
-                    local = idx - int(stt[s])
-                    w = int(T["recipes"][tvo[sType[s], a] + local])
-                    if w >> st.RC_SKIP_BIT:
+            rgb = T["run_gbase"].reshape(-1, NVMAX)
+            for r in range(nruns):
+                s_lo, s_hi = int(T["run_slo"][run0 + r]), int(T["run_shi"][run0 + r])
+                tv = tvo[int(T["run_type"][run0 + r])]
+                rec0, Ptot = int(tv[0]), int(tv[NV] - tv[0])
+                for u in range(Ptot):
+                    w = int(T["recipes"][rec0 + u])
+                    lo = w & 0xffffffff
+                    if lo >> st.RC_SKIP_BIT:
                         continue
-                    e = w & ((1 << st.RC_E_BITS) - 1)
-                    bi = (w >> st.RC_B_SHIFT) & ((1 << st.RC_B_BITS) - 1)
-                    ml = sNode[s + 1] + ((w >> st.RC_M_SHIFT) & ((1 << st.RC_M_BITS) - 1))
-                    ci = (w >> st.RC_C_SHIFT) & ((1 << st.RC_C_BITS) - 1)
-                    prev = (w >> st.RC_PREV_BIT) & 1
-                    plain = (w >> st.RC_PLAIN_BIT) & 1
-                    d = sD[e - 1, ml] if e else 0.0
-                    coef = 1.0 if plain else sB[bi] * (sHk[s] if prev else sHk[s + 1])
-                    out["jac"][base + idx] = coef * d + cst[ci]
+                    a = (w >> 32) & 0xff
+                    local = w >> 40
+                    Pa = int(tv[a + 1] - tv[a])
+                    e = lo & ((1 << st.RC_E_BITS) - 1)
+                    bi = (lo >> st.RC_B_SHIFT) & ((1 << st.RC_B_BITS) - 1)
+                    mloc = (lo >> st.RC_M_SHIFT) & ((1 << st.RC_M_BITS) - 1)
+                    ci = (lo >> st.RC_C_SHIFT) & ((1 << st.RC_C_BITS) - 1)
+                    prev = (lo >> st.RC_PREV_BIT) & 1
+                    plain = (lo >> st.RC_PLAIN_BIT) & 1
+                    for sc in range(s_lo, s_hi):
+                        ml = sNode[sc + 1] + mloc
+                        d = sD[e - 1, ml] if e else 0.0
+                        coef = 1.0 if plain else sB[bi] * (sHk[sc] if prev else sHk[sc + 1])
+                        out["jac"][int(rgb[run0 + r, a]) + local + (sc - s_lo) * Pa] = coef * d + cst[ci]
         partials[tile, :len(red)] = red
     # ---- border ----
     bv[0] = 1.0
