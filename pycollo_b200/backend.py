@@ -92,8 +92,13 @@ class Guess:
     def __init__(self, backend):
         ir = backend.ir
         self.tau, self.t0, self.tF, self.y, self.u, self.q, self.t = ([] for _ in range(7))
+        from .symbolic import _Resolver
+        problem_aux = dict(backend.ocp.auxiliary_data)
         for ph, uph in zip(ir.phases, backend.ocp.phases):
             g = uph.guess
+            aux = dict(problem_aux)
+            aux.update(uph.auxiliary_data)
+            self._resolver = _Resolver(aux, ())
             if g.time is None:
                 raise ValueError("A guess must be supplied.")
             time = np.asarray(g.time, dtype=np.float64)
@@ -111,17 +116,23 @@ class Guess:
             self.u.append(u[ph.u_needed])
             self.q.append(q[ph.q_needed])
             self.t.append(np.array([t0, tF])[np.array(ph.t_needed, dtype=bool)])
+        self._resolver = _Resolver(problem_aux, ())
         s = self._check(backend.ocp.guess.parameter_variables,
                         len(backend.ocp.parameter_variables))
         self.s = s[ir.s_needed] if len(s) else s
 
-    @staticmethod
-    def _check(guess, num_var, num_t=None):
+    def _check(self, guess, num_var, num_t=None):
+        """Shape check + numeric resolution of symbolic guesses through the
+        auxiliary data (``pycollo/guess.py:180-200``)."""
         if guess is None or num_var == 0:
             if num_var != 0:
                 raise ValueError("A guess must be supplied.")
             return np.empty((0, num_t)) if num_t is not None else np.empty((0,))
-        guess = np.asarray(guess, dtype=np.float64)
+        raw = np.asarray(guess, dtype=object)
+        flat = np.array([v if isinstance(v, (int, float, np.floating, np.integer))
+                         else float(self._resolver(v)) for v in raw.ravel()],
+                        dtype=np.float64)
+        guess = flat.reshape(raw.shape)
         if num_t is not None:
             if guess.shape != (num_var, num_t):
                 raise ValueError("A guess must be supplied for every symbol and time.")

@@ -1,0 +1,138 @@
+"""C-ABI library loads without a GPU and exports every symbol include/pcx.h
+declares; evaluations fail loudly (no CPU fallback); host-side API behaviour."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import sympy as sym
+
+import pycollo_b200
+from pycollo_b200 import OptimalControlProblem, examples
+from pycollo_b200 import engine as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = E.load_library()
+    header = open(os.path.join(ROOT, "include", "pcx.h")).read()
+    names = sorted(set(re.findall(r"\b(pcx_[a-z_0-9]+)\s*\(", header)))
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f"libpcx.so does not export {name}"
+    assert lib.pcx_version().startswith(b"pcx")
+    n = lib.pcx_table_count()
+    listed = {lib.pcx_table_name(i).decode(): lib.pcx_table_elem_size(i) for i in range(n)}
+    assert set(listed) == set(E._TABLE_DTYPES)
+    for k, size in listed.items():
+        assert np.dtype(E._TABLE_DTYPES[k]).itemsize == size, k
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    ocp = examples.brachistochrone()
+    ocp.initialise()
+    with pytest.raises(E.PcxError, match="no CPU fallback"):
+        ocp._backend.evaluate_J(np.zeros(125))
+
+
+def test_pcx_create_rejects_bad_spec():
+    lib = E.load_library()
+    h = ctypes.c_void_p()
+    assert lib.pcx_create(None, ctypes.byref(h)) == -1
+    spec = E._Spec(batch=0, num_tiles=1, threads=128, problem_header=b"x")
+    assert lib.pcx_create(ctypes.byref(spec), ctypes.byref(h)) == -1
+    assert b"bad batch" in lib.pcx_last_error(None)
+
+
+def test_settings_validation_mirrors_reference():
+    ocp = OptimalControlProblem("x")
+    assert ocp.settings.backend == "cuda"
+    for name in ("casadi", "hsad", "pycollo", "sympy"):       # test_initialisation.py:33-49
+        with pytest.raises(ValueError):
+            ocp.settings.backend = name
+    with pytest.raises(ValueError):
+        ocp.settings.quadrature_method = "gauss"
+    with pytest.raises(ValueError):
+        ocp.settings.scaling_method = "guess"
+    with pytest.raises(ValueError):
+        ocp.settings.derivative_level = 3
+    ocp.settings.quadrature_method = "RADAU"
+    assert ocp.settings.quadrature_method == "radau"
+
+
+def test_phase_symbols_and_errors():
+    x, v, u = sym.symbols("x v u")
+    ocp = OptimalControlProblem("p")
+    ph = ocp.new_phase("A", state_variables=[x, v], control_variables=u)
+    assert str(ph.initial_time_variable) == "t0_P0" and str(ph.final_time_variable) == "tF_P0"
+    assert str(ph.initial_state_variables.x) == "x_P0(t0)"
+    assert str(ph.final_state_variables[1]) == "v_P0(tF)"
+    ph.integrand_functions = [u ** 2]
+    assert str(ph.integral_variables[0]) == "q0_P0"
+    ph.state_equations = [v]
+    with pytest.raises(ValueError, match="state equation"):
+        ph._check_variables_and_equations()
+    ph.state_equations = {v: u, x: v}                 # dict form is ordered by state
+    assert ph.state_equations == (v, u)
+    with pytest.raises(ValueError):
+        ph.state_variables = [x, x]
+    with pytest.raises(NotImplementedError):
+        ocp.solve()
+
+
+def test_initialise_layout_and_scaling_against_golden():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "iteration_scaling_double_pendulum.npz"))
+    ocp = examples.double_pendulum()
+    ocp.initialise()
+    it = ocp._backend.mesh_iterations[0]
+    assert (it.num_x, it.num_c) == (190, 121)
+    np.testing.assert_array_equal(it.scaling.V, g["V"])
+    np.testing.assert_array_equal(it.scaling.r, g["r"])
+    np.testing.assert_allclose(it.scaling.V_inv, g["V_inv"], rtol=1e-15)
+    np.testing.assert_allclose(it.guess_x, g["x"], atol=1e-15)
+    np.testing.assert_allclose(it.guess_x_tilde, g["x_tilde"], atol=1e-15)
+    np.testing.assert_allclose(it.scaling.unscale_x(it.scaling.scale_x(g["x"])), g["x"],
+                               atol=1e-13)
+    # slices (tests/unit/test_iteration.py:210-234)
+    assert it.y_slices == [slice(0, 124)] and it.u_slices == [slice(124, 186)]
+    assert it.q_slices == [slice(186, 187)] and it.t_slices == [slice(187, 188)]
+    assert it.s_slice == slice(188, 190)
+    assert it.c_defect_slices == [slice(0, 120)] and it.c_integral_slices == [slice(120, 121)]
+    # state endpoint constraints are variable bounds, not rows of c
+    assert it.x_bnd_l[0] == it.x_bnd_u[0] == -0.25
+
+
+def test_undefined_symbol_is_reported():
+    x, u, k = sym.symbols("x u k")
+    ocp = OptimalControlProblem("p")
+    ph = ocp.new_phase("A", state_variables=[x], control_variables=[u])
+    ph.state_equations = [k * u]
+    ph.bounds.initial_time, ph.bounds.final_time = 0, 1
+    ph.bounds.state_variables = [[0, 1]]
+    ph.bounds.control_variables = [[0, 1]]
+    ph.guess.time = [0, 1]
+    ph.guess.state_variables = [[0, 1]]
+    ph.guess.control_variables = [[0, 0]]
+    ocp.objective_function = ph.final_state_variables[0]
+    with pytest.raises(ValueError, match="'k' is not defined"):
+        ocp.initialise()
+
+
+def test_nlp_callback_orderings_are_permutations():
+    from pycollo_b200.nlp import NlpCallbacks
+    ocp = examples.cart_pole_swing_up()
+    ocp.initialise()
+    it = ocp._backend.mesh_iterations[0]
+    cb = NlpCallbacks(it)
+    gr, gc = cb.jacobianstructure()
+    assert np.all(np.diff(gr * it.S.num_x + gc) > 0)          # row-major
+    hr, hc = cb.hessianstructure()
+    assert np.all(hr >= hc)                                     # lower triangle
+    assert sorted(cb.g_perm) == list(range(it.S.nnz_g))
+    assert sorted(cb.h_perm) == list(range(it.S.nnz_h))
+    assert pycollo_b200.__version__

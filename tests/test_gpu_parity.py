@@ -26,6 +26,14 @@ CASES = [
     ("double_pendulum", "lobatto", 6, RAGGED_NODES, RAGGED_SIZES, dict(max_tile_nodes=20)),
     ("double_pendulum", "radau", 10, 4, None, {}),
     ("cart_pole_swing_up", "lobatto", 2000, 4, None, {}),
+    ("free_flying_robot", "lobatto", 40, [4, 6] * 20, None, {}),
+    ("free_flying_robot", "radau", 300, 4, None, {}),
+    ("space_shuttle_reentry", "radau", 6, RAGGED_NODES, RAGGED_SIZES, dict(max_tile_nodes=20)),
+    ("space_shuttle_reentry", "lobatto", 400, 5, None, {}),
+    ("multiphase_sliding_mass", "lobatto", 7, 4, None, {}),
+    ("multiphase_sliding_mass", "radau", 200, 3, None, {}),
+    ("delta_iii_launch_vehicle", "lobatto", 4, 4, None, {}),
+    ("delta_iii_launch_vehicle", "lobatto", 500, 4, None, {}),
 ]
 
 
@@ -157,3 +165,41 @@ def test_full_size_config2_properties(cuda_device):
     assert max_err(h2, 3.0 * out["hess"][0]) <= 1e-13
     h0 = eng.eval_host(E.EVAL_HESS, x, 0.0 * lam, 0.0)["hess"][0]
     assert np.all(h0 == 0.0)
+
+
+def test_iteration_scaling_from_sparse_jacobian(cuda_device):
+    """N1 (scaling.py:346-430): W from row norms of the sparse G at the guess must
+    equal the reference formula applied to the oracle's (dense-able, small) G."""
+    from oracle.blockwise import BlockwiseNLP
+    from helpers import oracle_meshes
+    ocp = examples.free_flying_robot()
+    ocp.initialise()
+    backend = ocp._backend
+    it = backend.mesh_iterations[0]
+    it.generate_nlp()
+    B = BlockwiseNLP(ocp, backend.ir.full_bounds, oracle_meshes(it.mesh.p))
+    rows, cols = B.G_structure()
+    G = np.zeros((B.num_c, B.num_x))
+    G[rows, cols] = B.G_nonzeros(it.guess_x_tilde)
+    norm = np.sqrt((G ** 2).sum(axis=1))
+    ph = backend.ir.phases[0]
+    N = it.mesh.N[0]
+    W = it.scaling.W_ocp
+    np.testing.assert_allclose(W[:6], 1.0 / it.scaling.V_ocp[:6], rtol=1e-14)
+    p0 = 6 * (N - 1)
+    expect_path = 1.0 / norm[p0:p0 + 2 * N].reshape(2, N).mean(axis=1)
+    np.testing.assert_allclose(W[6:8], expect_path, rtol=1e-12)
+    np.testing.assert_allclose(W[8], 1.0 / it.scaling.V_ocp[10], rtol=1e-14)
+    # callbacks now run with that scaling
+    c = backend.evaluate_c(it.guess_x_tilde)
+    B2 = BlockwiseNLP(ocp, backend.ir.full_bounds, oracle_meshes(it.mesh.p), W_ocp=W, w=1.0)
+    assert max_err(c, B2.c(it.guess_x_tilde)) <= RTOL
+    cb = backend.nlp_callbacks()
+    lam = np.random.default_rng(0).standard_normal(it.num_c)
+    hr, hc = cb.hessianstructure()
+    H = np.zeros((it.num_x, it.num_x))
+    H[hr, hc] = cb.hessian(it.guess_x_tilde, lam, 0.5)
+    br, bc = B2.H_structure()
+    Hb = np.zeros_like(H)
+    Hb[bc, br] = B2.H_nonzeros(it.guess_x_tilde, 0.5, lam)      # lower triangle
+    assert max_err(H, Hb) <= RTOL
