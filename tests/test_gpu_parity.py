@@ -55,6 +55,10 @@ def test_all_callbacks_match_oracle(cuda_device, name, method, K, nodes, sizes, 
     rng = np.random.default_rng(7)
     for _ in range(2):
         x = rng.uniform(-0.5, 0.5, low.S.num_x)
+        if name == "delta_iii_launch_vehicle":
+            # keep the vehicle outside the Earth: exp(-(|r| - R_E)/h_0) overflows
+            # for random positions near the centre (in the oracle just the same)
+            x = rng.uniform(0.3, 0.45, low.S.num_x)
         lam = rng.standard_normal(low.S.num_c)
         sigma = float(rng.uniform(0.2, 2.0))
         out = eng.eval_host(ALL, x, lam, sigma)
