@@ -463,7 +463,7 @@ __device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
     // sections (one run per tile on a uniform mesh, plus a one-section run in the
     // first and last tile).  Thread t takes ONE slot u of the concatenated period
     // (all variables): its 64-bit recipe word is decoded once per run and the
-    // loop over the run's sections is  3 x LDS, DMUL, DFMA, STG + pointer bumps.
+    // loop over the run's sections is  2 x LDS, DMUL, DFMA, STG + pointer bumps.
     // Consecutive threads write consecutive addresses inside a variable's period,
     // and a variable's periods of consecutive sections are back to back.
     if (WANT_G) {
@@ -485,6 +485,13 @@ __device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
                 sc0 = s_lo + q;
                 if (q >= per) continue;
             }
+            // all sections of a run share one type, hence one order n_k: the
+            // first node of section sc is nd0 + (sc - s_lo) * (n_k - 1), so the
+            // staged-derivative pointer advances by a constant; constant-only
+            // slots read the 0.0 sentinel sB[0] with stride 0 and plain slots
+            // take their multiplier from the 1.0 sentinel sB[1], which keeps
+            // the loop free of divergent branches:  2 x LDS, DMUL, DFMA, STG
+            const int nstep = sSecOrder[s_lo + 1] - 1;
             for (int u = u0; u < Ptot; u += T) {
                 const unsigned long long w = pcx_ld_keep(p.recipes + rec0 + u, keep);
                 const u32 lo = (u32)w;
@@ -499,24 +506,18 @@ __device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
                     const int hsel = ((lo >> RC_PREV_BIT) & 1u) ? 0 : 1;
                     const bool plain = (lo >> RC_PLAIN_BIT) & 1u;
                     const double bcoef = sB[bi];
-                    const double* drow = sD + (e ? (e - 1) * nnp : 0) + mloc;
+                    const double* dp = e ? sD + (e - 1) * nnp + mloc + sSecNode[sc0 + 1] : sB;
+                    const int dstep = e ? per * nstep : 0;
+                    const double* hq = plain ? sB + 1 : sHk + hsel + sc0;
+                    const int hstep = plain ? 0 : per;
                     double* o = out_g + pcx_ld_keep(p.run_gbase + (i64)(run0 + r) * p.nvmax + a, keep) + local
                                 + (i64)(sc0 - s_lo) * Pa;
                     const int ostep = per * Pa;
-                    const int* nd = sSecNode + 1;
-                    const double* hk = sHk + hsel;
-                    int off = 0;
-                    if (e == 0) {
+                    const int cnt = (s_hi - sc0 + per - 1) / per;
 #pragma unroll 4
-                        for (int sc = sc0; sc < s_hi; sc += per, off += ostep) o[off] = cc;
-                    } else if (plain) {
-#pragma unroll 4
-                        for (int sc = sc0; sc < s_hi; sc += per, off += ostep)
-                            o[off] = drow[nd[sc]];
-                    } else {
-#pragma unroll 4
-                        for (int sc = sc0; sc < s_hi; sc += per, off += ostep)
-                            o[off] = __dmul_rn(bcoef, hk[sc]) * drow[nd[sc]] + cc;
+                    for (int it = 0; it < cnt; ++it) {
+                        *o = __dmul_rn(bcoef, *hq) * (*dp) + cc;
+                        o += ostep; dp += dstep; hq += hstep;
                     }
                 }
                 if (Ptot < T) break;

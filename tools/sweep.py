@@ -1,6 +1,6 @@
 """Tuning sweep of the fused G+H kernel on config 2 (threads, tiles/SM, reg cap)."""
 import itertools, json, os, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from helpers import build_case

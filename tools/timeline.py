@@ -1,6 +1,6 @@
 """Per-CTA phase timeline of the fused G+H kernel (debug build of the kernels)."""
 import ctypes, json, os, sys
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from helpers import build_case
