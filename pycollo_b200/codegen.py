@@ -71,6 +71,37 @@ def _gfun(name, values, default=0):
             f"{{ return {body}{default}; }}\n")
 
 
+def _share_reciprocals(repl, reduced):
+    """One fp64 division per distinct denominator: ``b**-n`` becomes
+    ``(1/b)**n`` with ``1/b`` a shared temporary (a DDIV costs ~10x a DMUL and
+    second derivatives of rational dynamics are full of ``b**-2``, ``b**-3``)."""
+    recip, out = {}, []
+
+    def fix(e):
+        for pw in sorted((q for q in e.atoms(sym.Pow)
+                          if q.exp.is_Integer and q.exp < 0),
+                         key=sym.default_sort_key):
+            b, n = pw.base, -int(pw.exp)
+            if b not in recip:
+                r = sym.Symbol(f"rc_{len(recip)}")
+                out.append((r, sym.Pow(b, -1)))
+                recip[b] = r
+            e = e.xreplace({pw: recip[b] ** n})
+        return e
+
+    for s_, e in repl:
+        if e.is_Pow and e.exp == -1:
+            recip.setdefault(e.base, s_)
+            if recip[e.base] is s_:
+                out.append((s_, e))
+            else:
+                out.append((s_, recip[e.base]))
+            continue
+        out.append((s_, fix(e)))
+    reduced = [fix(e) for e in reduced]
+    return out, reduced
+
+
 def _emit_program(inputs, outputs, indent="        "):
     """Straight-line program: ``inputs`` = [(symbol, c_expr)], ``outputs`` =
     [(c_lvalue, sympy expr)].  Shared CSE across all outputs; sin/cos of the
@@ -103,6 +134,7 @@ def _emit_program(inputs, outputs, indent="        "):
         exprs = [e.xreplace(trig_sub) for e in exprs]
     repl, reduced = sym.cse(exprs, symbols=sym.numbered_symbols("w_"),
                             order="none")
+    repl, reduced = _share_reciprocals(repl, reduced)
     for s, cexpr in inputs:
         lines.append(f"{indent}const double {s} = {cexpr};")
     lines.extend(pre)
@@ -164,7 +196,8 @@ def generate(ir, phase_derivs, point_derivs, structure):
            f"#define PCX_GS_VS 0\n#define PCX_GS_RS {NS}\n#define PCX_GS_W {2 * NS}\n"
            f"#define PCX_GS_WB {2 * NS + 1}\n",
            f"#define PCX_BV_PTVAL {structure.bv_ptval}\n#define PCX_BV_PTFN {structure.bv_ptfn}\n"
-           f"#define PCX_BV_PTD1 {structure.bv_ptd1}\n#define PCX_BV_PTD2 {structure.bv_ptd2}\n",
+           f"#define PCX_BV_PTD1 {structure.bv_ptd1}\n#define PCX_BV_PTD2 {structure.bv_ptd2}\n"
+           f"#define PCX_BV_IRR {structure.bv_irr0}\n",
            "#define PCX_FOREACH_PHASE(X) " + " ".join(f"X({q})" for q in range(P)) + "\n",
            "template <int P> struct PcxPhase;\n"]
     layouts = []

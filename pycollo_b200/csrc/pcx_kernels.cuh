@@ -66,17 +66,26 @@ __device__ __forceinline__ double pcx_block_sum(double v, double* scratch) {
 template <int N> struct PcxArr { double v[N > 0 ? N : 1]; };
 
 #ifdef PCX_DEBUG_TIMELINE
-// per-CTA phase timestamps (ns) into the partials scratch, 8 slots per tile
+// per-CTA phase timestamps (ns) into the partials scratch, 16 slots per tile
 __device__ __forceinline__ void pcx_stamp(const PcxParams& p, int tile, int k) {
     if (threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        p.partials[(i64)tile * 8 + k] = (double)(t & ((1ull << 40) - 1));
+        p.partials[(i64)tile * 16 + k] = (double)(t & ((1ull << 40) - 1));
     }
 }
 #define PCX_STAMP(k) pcx_stamp(p, tile, k)
+#define PCX_STAMP_B(k) pcx_stamp(p, 0, k)
+__device__ __forceinline__ void pcx_stamp_smid(const PcxParams& p, int tile) {
+    if (threadIdx.x == 0) {
+        unsigned id;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(id));
+        p.partials[(i64)tile * 16 + 10] = (double)id;
+    }
+}
 #else
 #define PCX_STAMP(k)
+#define PCX_STAMP_B(k)
 #endif
 
 // Engine tables (tile/section descriptors, recipes) are re-read by every launch
@@ -157,6 +166,31 @@ __device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
     const i64 sec_off = pb[Ph::PB_SECOFF];         // offset into sec_order/h/type
     const i64* sec_node = p.sec_node + sec_off + Ph::INDEX;   // K+1 per phase
     const unsigned long long keep = pcx_policy_keep();
+    const double* x = p.x + (i64)inst * p.num_x;
+    const double* lam = WANT_H ? p.lam + (i64)inst * p.num_c : nullptr;
+    {
+        // Speculative L2 prefetch of the tile's iterate/multiplier lines, issued
+        // before the tile descriptor (an L2 round trip) is known: tiles are
+        // balanced by node count (structure.py:_balanced_edges), so the first
+        // node of tile j of a phase is within one section of j*(N-1)/ntiles.
+        // A wrong guess costs nothing; a right one turns the DRAM latency of
+        // the dependent loads below into an L2 hit.
+        const int t_lo = (int)pb[Ph::PB_TILE0], nt = (int)pb[Ph::PB_TILE1] - t_lo;
+        const i64 est = (i64)((float)(tile - t_lo) * ((float)(N - 1) / (float)nt));
+        constexpr int NL = (T + 32) / 16;              // 128 B lines per stream
+        constexpr int NSTREAM = NV + (WANT_H ? NY + NP : 0);
+        for (int i = tid; i < NSTREAM * NL; i += T) {
+            const int st = i / NL;
+            i64 off = est + (i64)(i - st * NL) * 16;
+            if (off > N - 2) off = N - 2;
+            if (off < 0) off = 0;
+            const double* ptr;
+            if (st < NV) ptr = x + xo + (i64)st * N + off;
+            else if (st < NV + NY) ptr = lam + co + (i64)(st - NV) * (N - 1) + off;
+            else ptr = lam + co + (i64)NY * (N - 1) + (i64)(st - NV - NY) * N + off;
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr));
+        }
+    }
     const i64* td = p.tile_desc + (i64)tile * 8;   // phase,k0,k1,node0,nn,run0,run1,prev_rows
     const int k0 = (int)pcx_ld_keep(td + 1, keep), k1 = (int)pcx_ld_keep(td + 2, keep);
     const int nsec = k1 - k0;
@@ -167,17 +201,20 @@ __device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
     const int prev_rows = (int)pcx_ld_keep(td + 7, keep);   // defect rows of section k0-1
     const bool last_tile = (k1 == (int)K);
     const bool has_prev = (k0 > 0);
+    PCX_STAMP(7);
+#ifdef PCX_DEBUG_TIMELINE
+    pcx_stamp_smid(p, tile);
+#endif
     const int nnp = nn | 1;                        // odd stride: no bank conflicts
-
-    const double* x = p.x + (i64)inst * p.num_x;
-    const double* lam = WANT_H ? p.lam + (i64)inst * p.num_c : nullptr;
 
     // ---- shared memory carve-up ------------------------------------------
     double* sB = reinterpret_cast<double*>(smem_raw);          // btab
     double* sHk = sB + p.btab_len;                             // nsec+1 (prev first)
     double* sF = sHk + (nsec + 1);                             // NY * nnp
     double* sD = sF + (NEED_SF ? NY * nnp : 0);                // ND1V * nnp
-    double* sDS = sD + (WANT_G ? Ph::ND1V * nnp : 0);          // NDS * nnp
+    double* sDP = sD + (WANT_G ? Ph::ND1V * nnp : 0);          // ND1V * (nsec + 1)
+    const int nsp = nsec + 1;
+    double* sDS = sDP + (WANT_G ? Ph::ND1V * nsp : 0);         // NDS * nnp
     double* sLam = sDS + (WANT_G ? NDS * nnp : 0);             // NY * (nn + 16)
     const int lam_stride = nn + 16;
     double* sRed = sLam + (WANT_H ? NY * lam_stride : 0);      // T/32
@@ -200,11 +237,12 @@ __device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
     if (WANT_H) {
         // multipliers of the defect rows of sections k0-1 .. k1-1
         const int nrows = nn - 1 + prev_rows;
-        const i64 row0 = node0 - prev_rows;
+        const double* lp = lam + co + (node0 - prev_rows) + tid;
+#pragma unroll 1
+        for (int r = tid; r < nrows; r += T, lp += T) {
 #pragma unroll
-        for (int i = 0; i < NY; ++i)
-            for (int r = tid; r < nrows; r += T)
-                sLam[i * lam_stride + r] = lam[co + (i64)i * (N - 1) + row0 + r];
+            for (int i = 0; i < NY; ++i) sLam[i * lam_stride + r] = lp[(i64)i * (N - 1)];
+        }
     }
     for (int s = tid; s <= nsec; s += T) {
         const int k = k0 - 1 + s;                  // s = 0 is the previous section
@@ -215,6 +253,7 @@ __device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
     }
     if (tid == 0) sSecNode[nsec + 1] = nn - 1;
     __syncthreads();
+    PCX_STAMP(8);
     for (int s = tid; s < nsec; s += T) {
         const int b = sSecNode[s + 1], n = sSecOrder[s + 1];
         for (int m = 0; m < n - 1; ++m) sNodeSec[b + m] = s;
@@ -344,10 +383,16 @@ __device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
         }
         if (WANT_G) {
 #pragma unroll
+            // defect-family entries are staged already multiplied by the length
+            // of the section that owns the row: h_k for rows of the node's own
+            // section and, at a section's first node, h_{k-1} for the rows of
+            // the previous section (second copy, one slot per section)
             for (int k = 0; k < Ph::ND1V; ++k) {
                 const int fam = Ph::FAM(Ph::D1V_FN(k));
                 const double fac = fam == 0 ? hp : (fam == 1 ? 1.0 : -hp * wq);
-                sD[k * nnp + ml] = ps[Ph::OFF_D1V + k] * fac * D1V.v[k];
+                const double d = ps[Ph::OFF_D1V + k] * fac * D1V.v[k];
+                sD[k * nnp + ml] = fam == 0 ? d * h_k : d;
+                if (fam == 0 && mloc == 0) sDP[k * nsp + s] = d * h_pr;
             }
             int kd = 0, kr = 0;
 #pragma unroll
@@ -487,10 +532,10 @@ __device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
             }
             // all sections of a run share one type, hence one order n_k: the
             // first node of section sc is nd0 + (sc - s_lo) * (n_k - 1), so the
-            // staged-derivative pointer advances by a constant; constant-only
-            // slots read the 0.0 sentinel sB[0] with stride 0 and plain slots
-            // take their multiplier from the 1.0 sentinel sB[1], which keeps
-            // the loop free of divergent branches:  2 x LDS, DMUL, DFMA, STG
+            // staged-derivative pointer advances by a constant (1 for the
+            // previous-section copies); constant-only slots read the 0.0
+            // sentinel sB[0] with stride 0.  No divergent branch in the loop:
+            // LDS, DFMA, STG + two pointer bumps.
             const int nstep = sSecOrder[s_lo + 1] - 1;
             for (int u = u0; u < Ptot; u += T) {
                 const unsigned long long w = pcx_ld_keep(p.recipes + rec0 + u, keep);
@@ -503,21 +548,23 @@ __device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
                     const int bi = (lo >> RC_B_SHIFT) & ((1u << RC_B_BITS) - 1);
                     const int mloc = (lo >> RC_M_SHIFT) & ((1u << RC_M_BITS) - 1);
                     const double cc = cst[(lo >> RC_C_SHIFT) & ((1u << RC_C_BITS) - 1)];
-                    const int hsel = ((lo >> RC_PREV_BIT) & 1u) ? 0 : 1;
-                    const bool plain = (lo >> RC_PLAIN_BIT) & 1u;
-                    const double bcoef = sB[bi];
-                    const double* dp = e ? sD + (e - 1) * nnp + mloc + sSecNode[sc0 + 1] : sB;
-                    const int dstep = e ? per * nstep : 0;
-                    const double* hq = plain ? sB + 1 : sHk + hsel + sc0;
-                    const int hstep = plain ? 0 : per;
+                    const bool prev = (lo >> RC_PREV_BIT) & 1u;
+                    const double bcoef = sB[bi];                     // 1.0 for plain slots
+                    const double* dp = sB;
+                    int dstep = 0;
+                    if (e) {
+                        dp = prev ? sDP + (e - 1) * nsp + sc0
+                                  : sD + (e - 1) * nnp + mloc + sSecNode[sc0 + 1];
+                        dstep = prev ? per : per * nstep;
+                    }
                     double* o = out_g + pcx_ld_keep(p.run_gbase + (i64)(run0 + r) * p.nvmax + a, keep) + local
                                 + (i64)(sc0 - s_lo) * Pa;
                     const int ostep = per * Pa;
                     const int cnt = (s_hi - sc0 + per - 1) / per;
 #pragma unroll 4
                     for (int it = 0; it < cnt; ++it) {
-                        *o = __dmul_rn(bcoef, *hq) * (*dp) + cc;
-                        o += ostep; dp += dstep; hq += hstep;
+                        *o = bcoef * (*dp) + cc;
+                        o += ostep; dp += dstep;
                     }
                 }
                 if (Ptot < T) break;
@@ -540,38 +587,70 @@ __device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
 }
 
 // ---------------------------------------------------------------------------
-// Border pass: executed by the last CTA to finish (per instance).
+// Border pass: one dedicated CTA per instance (blockIdx.x == num_tiles, the
+// last one dispatched).  Everything that does not depend on the tiles -- point
+// variables, the point function, the multipliers, the border-map tables -- is
+// evaluated while the tiles run; the CTA then waits on the instance's ticket
+// until every tile that feeds it (reduction partials, end-node values, zeroed
+// gradient entries) has signalled, and applies the border map.  When no
+// reduction is selected only the first and last tile of each phase signal, so
+// the pass is off the kernel's critical path.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ u32 pcx_ld_acquire(const u32* ptr) {
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
+
+// tiles of phase q that signal the ticket for this output selection
+template <class Ph>
+__device__ __forceinline__ int pcx_signalling_tiles(int nt) {
+    constexpr int F = PCX_FLAGS;
+    if (pcx_need_red<Ph>()) return nt;
+    if ((F & PCX_F_H) || (F & PCX_F_GRAD)) return nt < 2 ? nt : 2;
+    return 0;
+}
+
+__device__ void pcx_border_map(const PcxParams& p, const int inst, const double* bv,
+                               const double* sRS, const bool commit, double* sink_slot)
+{
+    constexpr int F = PCX_FLAGS;
+    constexpr int T = PCX_THREADS;
+    double sink = 0.0;
+    for (int e = threadIdx.x; e < p.n_border; e += T) {
+        const int grp = p.border_grp[e];
+        const i64 slot = p.border_slot[e];
+        const int k0 = p.border_ptr[e], k1 = p.border_ptr[e + 1];
+        double* out;
+        if (grp == 0) { if (!(F & PCX_F_C)) continue; out = p.c + (i64)inst * p.num_c; }
+        else if (grp == 1) { if (!(F & PCX_F_G)) continue; out = p.gj + (i64)inst * p.nnz_g; }
+        else if (grp == 2) { if (!(F & PCX_F_H)) continue; out = p.hs + (i64)inst * p.nnz_h; }
+        else if (grp == 3) { if (!(F & PCX_F_J)) continue; out = p.jval + inst; }
+        else { if (!(F & PCX_F_GRAD)) continue; out = p.grad + (i64)inst * p.num_x; }
+        double acc = 0.0;
+        for (int k = k0; k < k1; ++k)
+            acc += p.border_coef[k] * bv[p.border_bv[k]] * sRS[p.border_rs[k]];
+        if (commit) out[slot] = acc; else sink += acc;
+    }
+    // the warm-up pass only pulls the map tables into L1/L2: its sums go to a
+    // scratch word nobody reads, which keeps the loads alive
+    if (!commit) *sink_slot = sink;
+}
+
 __device__ void pcx_border(const PcxParams& p, const int inst, double* scratch)
 {
     constexpr int F = PCX_FLAGS;
     constexpr int T = PCX_THREADS;
     const int tid = threadIdx.x;
-    double* bv = p.bv + (i64)inst * p.bv_size;
+    const double* bvg = p.bv + (i64)inst * p.bv_size;
     const double* x = p.x + (i64)inst * p.num_x;
     __shared__ double sRS[1 + PCX_NUM_PHASES];
-
-    // 1. final reductions: deterministic (fixed stride, fixed shuffle tree)
-    for (int q = 0; q < PCX_NUM_PHASES; ++q) {
-        bool need = false;
-#define PCX_CASE(P) if (q == P) need = pcx_need_red<PcxPhase<P> >();
-        PCX_FOREACH_PHASE(PCX_CASE)
-#undef PCX_CASE
-        const int nred = need ? PCX_PHASE_NRED(q) : 0;
-        const i64* pbq = pcx_c_pbase + PCX_PHASE_PBASE(q);
-        const int t_lo = (int)pbq[PCX_PB_TILE0], t_hi = (int)pbq[PCX_PB_TILE1];
-        for (int k = 0; k < nred; ++k) {
-            double acc = 0.0;
-            for (int t = t_lo + tid; t < t_hi; t += T)
-                acc += p.partials[((i64)inst * p.num_tiles + t) * p.nred_max + k];
-            const double r = pcx_block_sum(acc, scratch);
-            if (tid == 0) bv[PCX_PHASE_REDOFF(q) + k] = r;
-        }
-    }
-    // 2. point variables, multipliers and runtime scalars: one thread each, so
-    //    the dependent global loads overlap instead of queueing on thread 0
     __shared__ double sPt[PCX_NPOINT > 0 ? PCX_NPOINT : 1];
     __shared__ double sMult[1 + PCX_NB];
+    // the border-value vector lives in shared memory for the whole pass
+    double* bv = scratch + 32;
+
+    // ---- independent of the tiles ------------------------------------------
     for (int a = tid; a < PCX_NPOINT; a += T) {
         const double v = pcx_unscale(p.pt_scal[a], x[p.pt_x[a]], p.pt_scal[PCX_NPOINT + a]);
         sPt[a] = v;
@@ -600,47 +679,82 @@ __device__ void pcx_border(const PcxParams& p, const int inst, double* scratch)
                                       ps[PCX_PHASE_TINFO(qq) + 3]);
         sRS[q] = 0.5 * (tF - t0);
     }
-    // prefetch this thread's border-map entries while the point function runs
-    int e_grp = -1, e_k0 = 0, e_k1 = 0;
-    i64 e_slot = 0;
-    if (tid < p.n_border) {
-        e_grp = p.border_grp[tid];
-        e_slot = p.border_slot[tid];
-        e_k0 = p.border_ptr[tid];
-        e_k1 = p.border_ptr[tid + 1];
-    }
+    for (int i = 1 + tid; i < PCX_BV_PTVAL; i += T) bv[i] = 0.0;      // reductions (not yet known)
+    for (int i = PCX_BV_IRR + tid; i < p.bv_size; i += T) bv[i] = 0.0;
     __syncthreads();
     if (tid == 0)
         pcx_point_eval(sPt, sMult, bv + PCX_BV_PTFN, bv + PCX_BV_PTD1, bv + PCX_BV_PTD2);
     __syncthreads();
-    // 3. the border map
-    for (int e = tid; e < p.n_border; e += T) {
-        int grp = e_grp, k0 = e_k0, k1 = e_k1;
-        i64 slot = e_slot;
-        if (e != tid) {
-            grp = p.border_grp[e]; slot = p.border_slot[e];
-            k0 = p.border_ptr[e]; k1 = p.border_ptr[e + 1];
+    pcx_border_map(p, inst, bv, sRS, false, scratch + 31);   // warm the map tables
+
+    // ---- wait for the tiles that feed the border ------------------------------
+    int expected = 0;
+#define PCX_CASE(P) expected += pcx_signalling_tiles<PcxPhase<P> >(                      \
+        (int)(pcx_c_pbase[PCX_PHASE_PBASE(P) + PCX_PB_TILE1]                             \
+              - pcx_c_pbase[PCX_PHASE_PBASE(P) + PCX_PB_TILE0]));
+    PCX_FOREACH_PHASE(PCX_CASE)
+#undef PCX_CASE
+    if (expected > 0) {
+        if (tid == 0) {
+            while (pcx_ld_acquire(p.ticket + inst) < (u32)expected) __nanosleep(64);
         }
-        double* out;
-        if (grp == 0) { if (!(F & PCX_F_C)) continue; out = p.c + (i64)inst * p.num_c; }
-        else if (grp == 1) { if (!(F & PCX_F_G)) continue; out = p.gj + (i64)inst * p.nnz_g; }
-        else if (grp == 2) { if (!(F & PCX_F_H)) continue; out = p.hs + (i64)inst * p.nnz_h; }
-        else if (grp == 3) { if (!(F & PCX_F_J)) continue; out = p.jval + inst; }
-        else { if (!(F & PCX_F_GRAD)) continue; out = p.grad + (i64)inst * p.num_x; }
-        double acc = 0.0;
-        for (int k = k0; k < k1; ++k)
-            acc += p.border_coef[k] * bv[p.border_bv[k]] * sRS[p.border_rs[k]];
-        out[slot] = acc;
+        __syncthreads();
     }
+    PCX_STAMP_B(9);
+    // end-node values left by the first/last tiles (L2 reads: this CTA's L1 may
+    // hold nothing of them, but stay clear of it anyway)
+    for (int i = PCX_BV_IRR + tid; i < p.bv_size; i += T) bv[i] = __ldcg(bvg + i);
+    // final reductions: deterministic (fixed stride, fixed shuffle tree)
+    for (int q = 0; q < PCX_NUM_PHASES; ++q) {
+        bool need = false;
+#define PCX_CASE(P) if (q == P) need = pcx_need_red<PcxPhase<P> >();
+        PCX_FOREACH_PHASE(PCX_CASE)
+#undef PCX_CASE
+        const int nred = need ? PCX_PHASE_NRED(q) : 0;
+        const i64* pbq = pcx_c_pbase + PCX_PHASE_PBASE(q);
+        const int t_lo = (int)pbq[PCX_PB_TILE0], t_hi = (int)pbq[PCX_PB_TILE1];
+        for (int k = 0; k < nred; ++k) {
+            double acc = 0.0;
+            for (int t = t_lo + tid; t < t_hi; t += T)
+                acc += __ldcg(p.partials + ((i64)inst * p.num_tiles + t) * p.nred_max + k);
+            const double r = pcx_block_sum(acc, scratch);
+            if (tid == 0) bv[PCX_PHASE_REDOFF(q) + k] = r;
+        }
+    }
+    __syncthreads();
+    pcx_border_map(p, inst, bv, sRS, true, nullptr);
+    if (tid == 0) p.ticket[inst] = 0u;
 }
 
 extern "C" __global__ void __launch_bounds__(PCX_THREADS, PCX_MIN_BLOCKS)
 PCX_KERNEL_NAME(const PcxParams p)
 {
     extern __shared__ __align__(16) unsigned char pcx_smem[];
-    __shared__ int sLast;
-    const int tile = blockIdx.x, inst = blockIdx.y;
-    const int phase = (int)p.tile_desc[(long long)tile * 8];
+    int tile = blockIdx.x;
+    const int inst = blockIdx.y;
+    if (tile == p.num_tiles) {
+#ifndef PCX_DEBUG_NO_BORDER
+        pcx_border(p, inst, reinterpret_cast<double*>(pcx_smem));
+        PCX_STAMP_B(6);
+#endif
+        return;
+    }
+    // tiles are listed phase by phase: the phase follows from the constant-
+    // memory tile ranges, without a dependent global load.  The last tile of a
+    // phase trades places with the second one, so that both tiles the border
+    // pass may wait for (first and last: end-node values) are dispatched first.
+    int phase = 0;
+#pragma unroll
+    for (int q = 1; q < PCX_NUM_PHASES; ++q)
+        if (tile >= (int)pcx_c_pbase[PCX_PHASE_PBASE(q) + PCX_PB_TILE0]) phase = q;
+    {
+        const int t_lo = (int)pcx_c_pbase[PCX_PHASE_PBASE(phase) + PCX_PB_TILE0];
+        const int t_hi = (int)pcx_c_pbase[PCX_PHASE_PBASE(phase) + PCX_PB_TILE1];
+        if (t_hi - t_lo > 2) {
+            if (tile == t_lo + 1) tile = t_hi - 1;
+            else if (tile == t_hi - 1) tile = t_lo + 1;
+        }
+    }
     bool fence = false;
     switch (phase) {
 #define PCX_CASE(P) case P: fence = pcx_tile<PcxPhase<P> >(p, tile, inst, pcx_smem); break;
@@ -648,27 +762,13 @@ PCX_KERNEL_NAME(const PcxParams p)
 #undef PCX_CASE
         default: break;
     }
-#ifdef PCX_DEBUG_NO_TICKET
-    return;
-#endif
-    // ticket: the last CTA of this instance runs the border pass.  Only tiles
-    // whose writes the border pass depends on pay for a fence (it waits for all
-    // of the CTA's stores to drain); the bulk value stores need no ordering.
-    if (fence) __threadfence();
-    __syncthreads();
-    PCX_STAMP(4);
-    if (threadIdx.x == 0) {
-        const u32 t = atomicAdd(p.ticket + inst, 1u);
-        sLast = (t == (u32)p.num_tiles - 1u);
-    }
-    __syncthreads();
-    if (sLast) {
+    // only tiles whose writes the border pass depends on signal the ticket (and
+    // pay for a fence: it waits for all of the CTA's stores to drain); the bulk
+    // value stores need no ordering
+    if (fence) {
         __threadfence();
-#ifndef PCX_DEBUG_NO_BORDER
-        pcx_border(p, inst, reinterpret_cast<double*>(pcx_smem));
-#endif
-        if (threadIdx.x == 0) p.ticket[inst] = 0u;
-        PCX_STAMP(6);
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(p.ticket + inst, 1u);
     }
     PCX_STAMP(5);
 }

@@ -805,6 +805,7 @@ class NLPStructure:
         bv += len(ptd.d1)
         self.bv_ptd2 = bv               # contracted over (sigma*w*J, lam*W*b)
         bv += len(ptd.pairs)
+        self.bv_irr0 = bv               # end-node values written by the tiles
         for ip, (pd, t) in enumerate(zip(self.pd, self.ph)):
             t.bv_irr = []
             for end in range(2):

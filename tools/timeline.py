@@ -23,10 +23,11 @@ what = E.EVAL_JAC | E.EVAL_HESS
 for i in range(13):
     eng.eval_ptr(what, xs[i % R], lam=ls[i % R], jac=js[i % R], hess=hs[i % R], stream=st)
 torch.cuda.synchronize()
-buf = np.zeros(S.num_tiles * 8)
+buf = np.zeros(S.num_tiles * 16)
 eng.lib.pcx_debug_read_partials.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
 eng.lib.pcx_debug_read_partials(eng.h, buf.ctypes.data_as(ctypes.c_void_p), buf.size)
-t = buf.reshape(-1, 8)
+t = buf.reshape(-1, 16)
+raw_stamps = t.copy()
 t0 = t[:, 0].min()
 t = np.where(t == 0, np.nan, t)
 rel = (t - t0) / 1e3
@@ -35,13 +36,18 @@ rel[:, 6] = np.nan_to_num(rel[:, 6], nan=-1)
 print("tiles", S.num_tiles, "threads", threads, "min_blocks", mb)
 for k in range(6):
     col = rel[:, k][~np.isnan(rel[:, k])]
+    if col.size == 0: continue
     print(f"{names[k]:10s} min {col.min():7.2f} p10 {np.percentile(col,10):7.2f} med {np.median(col):7.2f} p90 {np.percentile(col,90):7.2f} max {col.max():7.2f} us")
+rel[:, 4] = rel[:, 3]      # (the pre-ticket stamp is gone: tiles no longer take a ticket)
 d = np.diff(rel[:, :6], axis=1)
 for k in range(5):
     print(f"phase {names[k]}->{names[k+1]:10s}: med {np.median(d[:,k]):6.2f} p90 {np.percentile(d[:,k],90):6.2f} max {d[:,k].max():6.2f} us")
 last = int(np.argmax(rel[:, 6]))
 print("border CTA", last, "border end", rel[last, 6], "its pre-ticket", rel[last, 4])
 print("kernel span (first start -> border end): %.2f us" % rel[last, 6])
+print("prologue split: td known med %.2f, loads arrived (1st barrier) med %.2f, node map built med %.2f us"
+      % (np.nanmedian(rel[:, 7]), np.nanmedian(rel[:, 8]), np.nanmedian(rel[:, 1])))
+print("border CTA: tiles signalled %.2f, border end %.2f, last tile end %.2f us" % (rel[0, 9], rel[0, 6], np.nanmax(rel[:, 5])))
 
 # write-only bandwidth ceiling
 buf = torch.empty(1 << 27, dtype=torch.float64, device="cuda")   # 1 GiB
@@ -59,3 +65,13 @@ e0.record()
 for i in range(60): small[i % 6].fill_(2.0)
 e1.record(); torch.cuda.synchronize()
 print("35 MB fill_ in ring: %.2f us each" % (1e3 * e0.elapsed_time(e1) / 60))
+
+# per-SM view: CTAs per SM and how the node phase stretches with them
+smid = raw_stamps[:, 10].astype(int)
+cnt = np.bincount(smid)
+print("CTAs per SM: min %d max %d (SMs used %d)" % (cnt[cnt > 0].min(), cnt.max(), (cnt > 0).sum()))
+node_d = rel[:, 2] - rel[:, 1]
+slow = np.argsort(-node_d)[:12]
+print("slowest node phases:", [(int(i), int(smid[i]), round(float(node_d[i]), 2)) for i in slow])
+per_sm_end = np.array([rel[smid == s_, 5].max() for s_ in np.flatnonzero(cnt)])
+print("per-SM last CTA end: min %.2f med %.2f max %.2f us" % (per_sm_end.min(), np.median(per_sm_end), per_sm_end.max()))
