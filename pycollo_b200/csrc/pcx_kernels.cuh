@@ -135,12 +135,12 @@ __host__ __device__ constexpr bool pcx_need_red() {
 }
 
 // ---------------------------------------------------------------------------
-// One tile of phase Ph.  Returns true when the tile wrote something the border
-// pass reads (reduction partials, end-node values) or that it overwrites
-// (gradient zeros), i.e. when its writes must be fenced before the ticket.
+// One tile of phase Ph.  A tile that writes something the border pass reads
+// (reduction partials, end-node values) or overwrites (gradient zeros) fences
+// those writes and bumps the instance's ticket as soon as its node phase ends.
 // ---------------------------------------------------------------------------
 template <class Ph>
-__device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
+__device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
                          unsigned char* smem_raw)
 {
     constexpr int F = PCX_FLAGS;
@@ -455,6 +455,25 @@ __device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
     __syncthreads();
 
     PCX_STAMP(2);
+    // ---- reductions -> per-tile partials, and the signal to the border CTA ------
+    // Everything the border pass reads from a tile (partials, end-node values,
+    // zeroed gradient entries) exists once the node phase is over: signalling
+    // here, before the bulk of the value stores is issued, keeps the fence
+    // (which waits for the CTA's outstanding stores) short.
+    if (pcx_need_red<Ph>()) {
+#pragma unroll
+        for (int k = 0; k < Ph::NRED; ++k) {
+            const double r = pcx_block_sum(red[k], sRed);
+            if (tid == 0)
+                p.partials[((i64)inst * p.num_tiles + tile) * p.nred_max + k] = r;
+        }
+    }
+    if (pcx_need_red<Ph>() || (WANT_H && (k0 == 0 || last_tile))
+        || (WANT_GRAD && (k0 == 0 || last_tile || tile == 0))) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(p.ticket + inst, 1u);
+    }
     // ---- row-oriented contractions: defect rows of c, t/s columns of G -------
     if (NEED_ROWS) {
         for (int r = tid; r < nn - 1; r += T) {
@@ -573,17 +592,6 @@ __device__ bool pcx_tile(const PcxParams& p, const int tile, const int inst,
     }
 
     PCX_STAMP(3);
-    // ---- reductions -> per-tile partials ---------------------------------------
-    if (pcx_need_red<Ph>()) {
-#pragma unroll
-        for (int k = 0; k < Ph::NRED; ++k) {
-            const double r = pcx_block_sum(red[k], sRed);
-            if (tid == 0)
-                p.partials[((i64)inst * p.num_tiles + tile) * p.nred_max + k] = r;
-        }
-    }
-    return pcx_need_red<Ph>() || (WANT_H && (k0 == 0 || last_tile))
-           || (WANT_GRAD && (k0 == 0 || last_tile || tile == 0));
 }
 
 // ---------------------------------------------------------------------------
@@ -730,9 +738,12 @@ extern "C" __global__ void __launch_bounds__(PCX_THREADS, PCX_MIN_BLOCKS)
 PCX_KERNEL_NAME(const PcxParams p)
 {
     extern __shared__ __align__(16) unsigned char pcx_smem[];
-    int tile = blockIdx.x;
+    // large meshes: the border CTA is dispatched first and works in the shadow
+    // of the tiles; small ones: last, so that it never holds a slot a tile of
+    // its own instance could use
+    int tile = p.border_first ? (int)blockIdx.x - 1 : (int)blockIdx.x;
     const int inst = blockIdx.y;
-    if (tile == p.num_tiles) {
+    if (tile == (p.border_first ? -1 : p.num_tiles)) {
 #ifndef PCX_DEBUG_NO_BORDER
         pcx_border(p, inst, reinterpret_cast<double*>(pcx_smem));
         PCX_STAMP_B(6);
@@ -755,20 +766,11 @@ PCX_KERNEL_NAME(const PcxParams p)
             else if (tile == t_hi - 1) tile = t_lo + 1;
         }
     }
-    bool fence = false;
     switch (phase) {
-#define PCX_CASE(P) case P: fence = pcx_tile<PcxPhase<P> >(p, tile, inst, pcx_smem); break;
+#define PCX_CASE(P) case P: pcx_tile<PcxPhase<P> >(p, tile, inst, pcx_smem); break;
         PCX_FOREACH_PHASE(PCX_CASE)
 #undef PCX_CASE
         default: break;
-    }
-    // only tiles whose writes the border pass depends on signal the ticket (and
-    // pay for a fence: it waits for all of the CTA's stores to drain); the bulk
-    // value stores need no ordering
-    if (fence) {
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) atomicAdd(p.ticket + inst, 1u);
     }
     PCX_STAMP(5);
 }

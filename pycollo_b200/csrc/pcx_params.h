@@ -37,7 +37,8 @@ struct PcxParams {
     double* jval;           // (batch)
     double* grad;           // (batch, num_x)
     i64 num_x, num_c, num_dy, nnz_g, nnz_h;
-    int num_tiles, batch, nvmax, n_border, bv_size, nred_max, btab_len, pad0;
+    int num_tiles, batch, nvmax, n_border, bv_size, nred_max, btab_len;
+    int border_first;       // 1: the border CTA is blockIdx.x == 0 (resident from the start)
     // tiles
     const i64* tile_desc;   // 8 per tile: phase,k0,k1,node0,nn,run0,run1,-
     const int* run_slo; const int* run_shi; const int* run_type;

@@ -704,6 +704,7 @@ class NLPStructure:
         T = self.threads
         tiles = []
         total_nodes = sum(t.N for t in self.ph)
+        border_phase = int(np.argmax([t.N for t in self.ph]))
         for ip, (pd, t) in enumerate(zip(self.pd, self.ph)):
             cap = max_tile_nodes or T
             cap = min(cap, max(16, smem_budget // self.bytes_per_node(pd)))
@@ -719,6 +720,11 @@ class NLPStructure:
                     m = -(-m // RESIDENT_CTAS) * RESIDENT_CTAS   # whole waves
                 want = max(want, int(round(m * sm_count * share)))
             want = min(want, t.K)
+            # the border pass is a CTA of its own (csrc/pcx_kernels.cuh): leave
+            # it one slot of the wave so that it is resident from the start
+            if (total_nodes >= 32 * sm_count and ip == border_phase and want > 2
+                    and int(np.ceil((t.N - 1) / (want - 1))) + 1 <= cap):
+                want -= 1
             edges = self._balanced_edges(t.sec_node, want, cap)
             for k0, k1 in zip(edges[:-1], edges[1:]):
                 tiles.append((ip, int(k0), int(k1)))
