@@ -132,6 +132,25 @@ int pcx_eval_jac_hess(pcx_engine* e, const double* x, const double* lam,
                       const double* sigma, double* jac, double* hess,
                       int space, void* stream);
 
+/* ---- mesh-refinement error -----------------
+ * Replaces PattersonRaoMeshRefinement.generate_dy_ph_callables +
+ * phase_mesh_error (pycollo/mesh_refinement.py:88-158, 206-240) for an engine
+ * that was created on the p+1 ("ph") mesh with unit scaling (V=1, r=0, W=1,
+ * as mesh_refinement.py:149-150 substitutes).  x_ph is the solution
+ * interpolated to the ph mesh in the engine's x layout.  One fused pass
+ * evaluates dy_ph at every ph node and contracts it with the ph integration
+ * blocks (the defect rows of the ph mesh ARE y_k + stretch*I*dy - Y), then a
+ * section-parallel kernel forms, per phase p and section k,
+ *   abs_err[err_off_p + (k*n_y + i)*mmax_p + l] = |Y_hat - Y|      (:216-226)
+ *   rel_err[...] = abs / (1 + (max_l |Y| + 1))   (sic, :224, :229-234)
+ *   max_rel[sec_off_p + k] = max over states and nodes            (:237-240)
+ * with mmax_p = max_k N_k(ph) - 1 and zeros in the unused tail, phases
+ * concatenated.  Any output may be NULL.                                     */
+int pcx_mesh_error(pcx_engine* e, const double* x_ph, double* abs_err,
+                   double* rel_err, double* max_rel, int space, void* stream);
+/* lengths (per instance) of abs_err/rel_err and of max_rel                    */
+int pcx_mesh_error_sizes(const pcx_engine* e, int64_t* n_err, int64_t* n_sections);
+
 /* Sizes (per instance) -- Casadi.evaluate_G_num_nonzero backend.py:1763-1771 */
 int pcx_sizes(const pcx_engine* e, int64_t* num_x, int64_t* num_c, int64_t* num_dy,
               int64_t* nnz_jac, int64_t* nnz_hess, int32_t* batch);

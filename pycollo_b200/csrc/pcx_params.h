@@ -56,6 +56,7 @@ struct PcxParams {
     double* partials; u32* ticket; double* bv;
     const int* border_grp; const i64* border_slot; const int* border_ptr;
     const int* border_bv; const int* border_rs; const double* border_coef;
+    const i64* err_desc;    // mesh-error pass, 12 per phase: x_off,c_off,N,K,NY,sec_node_off,err_off,sec_off,mmax
     const i64* pt_x;        // x index of each point variable
     const double* pt_scal;  // V then r of each point variable
 };

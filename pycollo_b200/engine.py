@@ -85,6 +85,8 @@ def load_library(rebuild=False):
     lib.pcx_launch_count.restype = i64
     lib.pcx_synchronize.argtypes = [vp, vp]
     lib.pcx_flush_l2.argtypes = [vp, i64, vp]
+    lib.pcx_mesh_error.argtypes = [vp, dp, dp, dp, dp, i32, vp]
+    lib.pcx_mesh_error_sizes.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     _LIB = lib
     return lib
 
@@ -97,7 +99,7 @@ _TABLE_DTYPES = {
     "btab": np.float64, "order_a_off": np.int32, "order_w_off": np.int32,
     "pbase": np.int64, "border_grp": np.int32, "border_slot": np.int64,
     "border_ptr": np.int32, "border_bv": np.int32, "border_rs": np.int32,
-    "pt_x": np.int64,
+    "pt_x": np.int64, "err_desc": np.int64,
 }
 
 
@@ -148,6 +150,18 @@ def build_tables(S, layouts):
     t["border_grp"], t["border_slot"] = S.border_grp, S.border_slot
     t["border_ptr"], t["border_bv"], t["border_rs"] = S.border_ptr, S.border_bv, S.border_rs
     t["pt_x"] = S.pt_x
+    # mesh-error pass (pcx_mesh_error): per phase x_off, c_off, N, K, n_y, offset
+    # of the phase's K+1 section-start nodes in sec_node, offsets of its block in
+    # the error arrays / per-section maxima, and mmax = max_k N_k - 1
+    ed = np.zeros((len(S.ph), 12), dtype=np.int64)
+    eo = so = 0
+    for ip, (ph, lay) in enumerate(zip(S.ph, layouts)):
+        mmax = int(np.max(ph.sec_order)) - 1
+        ed[ip, :9] = (ph.x_off, ph.c_off, ph.N, ph.K, lay.pd.NY, ph.sec_off + ip,
+                      eo, so, mmax)
+        eo += ph.K * lay.pd.NY * mmax
+        so += ph.K
+    t["err_desc"] = ed.ravel()
     return {k: np.ascontiguousarray(v, dtype=_TABLE_DTYPES[k]) for k, v in t.items()}
 
 
@@ -324,6 +338,39 @@ class Engine:
             _ptr(out.get("grad")), _ptr(out.get("c")), _ptr(out.get("dy")),
             _ptr(out.get("jac")), _ptr(out.get("hess")), PCX_HOST, None), "pcx_eval")
         return out
+
+    def mesh_error_sizes(self):
+        ne, ns = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self.lib.pcx_mesh_error_sizes(self.h, ctypes.byref(ne), ctypes.byref(ns)),
+                    "pcx_mesh_error_sizes")
+        return int(ne.value), int(ns.value)
+
+    def mesh_error_host(self, x_ph):
+        """``pcx_mesh_error`` on host arrays: per phase ``(abs, rel, max_rel)`` with
+        ``abs/rel`` of shape ``(K, n_y, mmax)`` and ``max_rel`` of shape ``(K,)``
+        (``pycollo/mesh_refinement.py:206-240``); a leading batch axis if batch > 1."""
+        S, B = self.S, self.batch
+        x = np.ascontiguousarray(x_ph, dtype=np.float64).reshape(B, S.num_x)
+        ne, ns = self.mesh_error_sizes()
+        a, r, m = np.empty((B, ne)), np.empty((B, ne)), np.empty((B, ns))
+        self._check(self.lib.pcx_mesh_error(self.h, _ptr(x), _ptr(a), _ptr(r), _ptr(m),
+                                            PCX_HOST, None), "pcx_mesh_error")
+        ed = self.tables["err_desc"].reshape(-1, 12)
+        out = []
+        for row in ed:
+            K, NY, eo, so, mmax = int(row[3]), int(row[4]), int(row[6]), int(row[7]), int(row[8])
+            shp = (B, K, NY, mmax)
+            pa = a[:, eo:eo + K * NY * mmax].reshape(shp)
+            pr = r[:, eo:eo + K * NY * mmax].reshape(shp)
+            pm = m[:, so:so + K]
+            out.append((pa[0], pr[0], pm[0]) if B == 1 else (pa, pr, pm))
+        return out
+
+    def mesh_error_ptr(self, x_ph, abs_err=None, rel_err=None, max_rel=None,
+                       space=PCX_DEVICE, stream=None):
+        self._check(self.lib.pcx_mesh_error(
+            self.h, _ptr(x_ph), _ptr(abs_err), _ptr(rel_err), _ptr(max_rel), space,
+            ctypes.c_void_p(stream) if stream else None), "pcx_mesh_error")
 
     # -- raw pointers (device tensors, pinned buffers) ------------------------
     def eval_ptr(self, what, x, lam=None, sigma=None, f=None, grad=None, c=None,

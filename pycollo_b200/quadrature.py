@@ -146,11 +146,40 @@ class Quadrature:
         self.method = method
         self._cache = {}
 
+    @classmethod
+    def adopt(cls, source, method=None):
+        """Drop-in path: take points / weights / Butcher arrays from a quadrature
+        object produced elsewhere -- the reference's own ``Quadrature``
+        (``pycollo/quadrature.py:40-114``: ``quadrature_point(order)``,
+        ``quadrature_weight(order)``, ``butcher_array(order)``) or a mapping with
+        ``points_<n>``, ``weights_<n>``, ``butcher_<n>`` entries -- instead of
+        generating them, so that the integration blocks ``A(N_k) * h_k`` are the
+        reference's to the last bit (including the digits its ill-conditioned
+        solve loses at high order)."""
+        if method is None:
+            method = getattr(source, "method", None) or \
+                source.backend.ocp.settings.quadrature_method
+        self = cls(method)
+        self._source = source
+        return self
+
+    def _adopted(self, order):
+        src = self._source
+        if hasattr(src, "butcher_array"):
+            return {"points": np.asarray(src.quadrature_point(order), dtype=np.float64),
+                    "weights": np.asarray(src.quadrature_weight(order), dtype=np.float64),
+                    "butcher": np.asarray(src.butcher_array(order), dtype=np.float64)}
+        return {"points": np.asarray(src[f"points_{order}"], dtype=np.float64),
+                "weights": np.asarray(src[f"weights_{order}"], dtype=np.float64),
+                "butcher": np.asarray(src[f"butcher_{order}"], dtype=np.float64)}
+
     def _tables(self, order):
         order = int(order)
         if order < 2:
             raise ValueError("a mesh section needs at least two nodes")
         tab = self._cache.get(order)
+        if tab is None and getattr(self, "_source", None) is not None:
+            tab = self._cache[order] = self._adopted(order)
         if tab is None:
             tab = (self._lobatto(order) if self.method == LOBATTO
                    else self._radau(order))

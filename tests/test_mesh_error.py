@@ -1,0 +1,160 @@
+"""Mesh-refinement error.
+
+Golden fixtures ``tests/golden/mesh_error_*.npz`` hold the outputs of the
+reference's own ``PattersonRaoMeshRefinement.phase_mesh_error``
+(``pycollo/mesh_refinement.py:206-240``) executed on the reference's own ph mesh
+(``oracle/make_golden.py``).  CPU: the oracle restatement reproduces them
+bit-for-bit.  GPU: ``pcx_mesh_error`` reproduces them to 1e-12 relative /
+1e-14 absolute from ``x_ph`` alone (it evaluates dy_ph itself)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import GOLDEN
+from oracle import mesh_error as OM
+from pycollo_b200 import examples
+from pycollo_b200.mesh import Mesh, PhaseMesh
+from pycollo_b200.quadrature import Quadrature
+
+CASES = [("robot_lobatto", "free_flying_robot", "lobatto"),
+         ("robot_radau", "free_flying_robot", "radau"),
+         ("shuttle_lobatto", "space_shuttle_reentry", "lobatto"),
+         ("multiphase_lobatto", "multiphase_sliding_mass", "lobatto")]
+
+
+def _load(tag):
+    return np.load(f"{GOLDEN}/mesh_error_{tag}.npz")
+
+
+def _problem(name, method):
+    ocp = getattr(examples, name)()
+    ocp.settings.quadrature_method = method
+    ocp.settings.scaling_method = "none"
+    return ocp
+
+
+@pytest.mark.parametrize("tag,problem,method", CASES)
+def test_oracle_reproduces_reference_mesh_error(tag, problem, method):
+    g = _load(tag)
+    ocp = _problem(problem, method)
+    nodes_ph = OM.ph_section_nodes(g["section_nodes"])
+    quad = Quadrature.adopt(np.load(f"{GOLDEN}/quadrature_{method}.npz"), method)
+    ph = Mesh(quad, [PhaseMesh(len(nodes_ph), g["section_sizes"], nodes_ph)
+                     for _ in ocp.phases], 2, 17)
+    from pycollo_b200.backend import lower_problem
+    low = lower_problem(ocp, ph.p)
+    for ip, (irp, t) in enumerate(zip(low.ir.phases, low.S.ph)):
+        N = t.N
+        sI = sp.csr_matrix((g[f"sI_data_{ip}"], g[f"sI_indices_{ip}"], g[f"sI_indptr_{ip}"]),
+                           shape=(N - 1, N))
+        # with the reference's quadrature tables adopted, the ph mesh operators
+        # ARE the reference's (same single rounded product A * h_k, mesh.py:300)
+        assert np.max(np.abs((ph.sI_matrix[ip] - sI).toarray())) <= 1e-16
+        own = Mesh(Quadrature(method), [PhaseMesh(len(nodes_ph), g["section_sizes"], nodes_ph)], 2, 17)
+        assert np.max(np.abs((own.sI_matrix[0] - sI).toarray())) < 3e-12   # own tables: see DESIGN.md section 1
+        y_ph = g["x_ph"][t.x_off:t.x_off + irp.n_y * N].reshape(irp.n_y, N)
+        a, r, m = OM.phase_mesh_error(g[f"dy_{ip}"], y_ph, sI, float(g[f"stretch_{ip}"]),
+                                      nodes_ph, ph.mesh_index_boundaries[ip])
+        assert np.array_equal(a, g[f"abs_{ip}"])
+        assert np.array_equal(r, g[f"rel_{ip}"])
+        assert np.array_equal(m, g[f"max_{ip}"])
+        assert m.max() > 1e-6          # the fixture is not trivially zero
+
+
+def test_ph_mesh_has_one_more_node_per_section():
+    from pycollo_b200.mesh_refinement import create_ph_mesh
+    quad = Quadrature("lobatto")
+    mesh = Mesh(quad, [PhaseMesh(4, [0.1, 0.2, 0.3, 0.4], [3, 5, 2, 4])])
+    ph = create_ph_mesh(mesh)
+    assert list(ph.N_K[0]) == [4, 6, 3, 5]
+    assert np.allclose(ph.h_K[0], mesh.h_K[0])
+    assert ph.N[0] == mesh.N[0] + 4
+    # section boundaries coincide (mesh_refinement.py:164-166)
+    assert np.allclose(ph.tau[0][ph.mesh_index_boundaries[0]],
+                       mesh.tau[0][mesh.mesh_index_boundaries[0]])
+
+
+def test_polynomial_refit_reproduces_polynomial_solutions():
+    """solution_abc.py:60-101: on a section of N_k nodes a degree N_k-1 state
+    derivative is re-fitted exactly, so y_ph equals the true polynomial."""
+    quad = Quadrature("lobatto")
+    mesh = Mesh(quad, [PhaseMesh(3, [0.2, 0.5, 0.3], [4, 5, 3])])
+    tau = mesh.tau[0]
+    T = 3.0
+    coef = np.array([0.3, -1.0, 0.5])                     # y = c0 + c1 t + c2 t^2, t = tau*T/2
+    t = tau * T / 2
+    y = (coef[0] + coef[1] * t + coef[2] * t * t)[None, :]
+    dy = (coef[1] + 2 * coef[2] * t)[None, :]
+    u = np.cos(tau)[None, :]
+    yp, up = OM.fit_section_polys(tau, y, dy, u, T, mesh.mesh_index_boundaries[0], mesh.N_K[0])
+    from pycollo_b200.mesh_refinement import create_ph_mesh
+    ph = create_ph_mesh(mesh)
+    y_ph = OM.interpolate_to_ph(y, yp, mesh.mesh_index_boundaries[0],
+                                ph.mesh_index_boundaries[0], ph.tau[0])
+    t_ph = ph.tau[0] * T / 2
+    assert np.allclose(y_ph[0], coef[0] + coef[1] * t_ph + coef[2] * t_ph ** 2, atol=1e-13)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,problem,method", CASES)
+def test_gpu_mesh_error_matches_reference(tag, problem, method):
+    from pycollo_b200.mesh_refinement import MeshErrorEvaluator
+    g = _load(tag)
+    ocp = _problem(problem, method)
+    quad = Quadrature.adopt(np.load(f"{GOLDEN}/quadrature_{method}.npz"), method)
+    mesh = Mesh(quad, [PhaseMesh(len(g["section_nodes"]), g["section_sizes"], g["section_nodes"])
+                       for _ in ocp.phases], 2, 16)
+    ev = MeshErrorEvaluator(ocp, mesh)
+    res = ev(g["x_ph"])
+    for ip, (a, r, m) in enumerate(res):
+        ea, er, em = g[f"abs_{ip}"], g[f"rel_{ip}"], g[f"max_{ip}"]
+        assert a.shape == ea.shape and m.shape == em.shape
+        # 1e-12 relative / 1e-14 absolute (BASELINE north star), scaled by |Y|
+        yscale = 1.0 + np.max(np.abs(g["x_ph"]))
+        assert np.max(np.abs(a - ea)) <= 1e-12 * yscale
+        assert np.max(np.abs(r - er)) <= 1e-12
+        assert np.max(np.abs(m - em)) <= 1e-12
+        assert np.all(a[ea == 0.0] == 0.0)             # unused tail stays zero
+
+
+@pytest.mark.gpu
+def test_gpu_mesh_refinement_from_solution():
+    """Solution -> construct_x_ph -> device error pass against the oracle chain."""
+    from oracle.blockwise import BlockwiseNLP
+    from pycollo_b200.backend import Cuda
+    from pycollo_b200.solution import Solution
+    ocp = examples.free_flying_robot()
+    ocp.settings.scaling_method = "none"
+    examples.set_mesh(ocp, 12, 5)
+    backend = Cuda(ocp)
+    for step in ("create_bounds", "create_scaling", "create_quadrature",
+                 "create_initial_mesh", "create_guess", "create_mesh_iterations"):
+        getattr(backend, step)()
+    it = backend.current_iteration
+    it.generate_nlp()
+    rng = np.random.default_rng(5)
+    x = it.guess_x_tilde + 0.05 * rng.standard_normal(it.S.num_x)
+    sol = Solution(it, x)
+    mr = sol.refine_mesh()
+    # oracle chain on the same x
+    ip = 0
+    pd = sol.phase_data[ip]
+    mesh = it.mesh
+    yp, up = OM.fit_section_polys(pd.tau, pd.y, pd.dy, pd.u, pd.T,
+                                  mesh.mesh_index_boundaries[ip], mesh.N_K[ip])
+    ph = mr.ph_mesh
+    y_ph = OM.interpolate_to_ph(pd.y, yp, mesh.mesh_index_boundaries[ip],
+                                ph.mesh_index_boundaries[ip], ph.tau[ip])
+    u_ph = OM.interpolate_to_ph(pd.u, up, mesh.mesh_index_boundaries[ip],
+                                ph.mesh_index_boundaries[ip], ph.tau[ip])
+    assert np.allclose(y_ph, mr.y_ph[ip], atol=1e-13)
+    assert np.allclose(u_ph, mr.u_ph[ip], atol=1e-13)
+    low = mr.evaluator.low
+    B = BlockwiseNLP(ocp, low.ir.full_bounds,
+                     [dict(N=m.N, sI=m.sI_matrix, sA=m.sA_matrix, W=m.W_matrix) for m in ph.p],
+                     scaling_method="none")
+    dy = B.dy(mr.x_ph)
+    a, r, m = OM.phase_mesh_error(dy[:pd.y.shape[0] * ph.N[ip]], mr.y_ph[ip], ph.sI_matrix[ip],
+                                  pd.stretch, ph.N_K[ip], ph.mesh_index_boundaries[ip])
+    assert np.max(np.abs(mr.absolute_mesh_errors[ip] - a)) <= 1e-12 * (1 + np.abs(mr.x_ph).max())
+    assert np.max(np.abs(mr.maximum_relative_mesh_errors[ip] - m)) <= 1e-12
