@@ -98,7 +98,8 @@ def test_config2_counts_and_tiling():
     assert (S.num_x, S.num_c) == (500001, 399997)
     assert S.nnz_g == 38 * (N - 1) + N + 1 == 3899963
     assert S.nnz_h == 5 * N == 500000
-    assert S.num_tiles % 148 == 0 and S.max_tile_nodes <= S.threads
+    # one wave of 148 x 6 CTAs: 887 tiles + the border CTA
+    assert (S.num_tiles + 1) % 148 == 0 and S.max_tile_nodes <= S.threads
     # tiles partition the sections; runs partition the tiles
     assert S.tile_k0[0] == 0 and S.tile_k1[-1] == 33333
     assert np.array_equal(S.tile_k0[1:], S.tile_k1[:-1])
