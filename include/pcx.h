@@ -132,6 +132,24 @@ int pcx_eval_jac_hess(pcx_engine* e, const double* x, const double* lam,
                       const double* sigma, double* jac, double* hess,
                       int space, void* stream);
 
+/* ---- one mesh over several GPUs (BASELINE config 4) --
+ * Every rank creates the same engine (same problem, same mesh) and then
+ * restricts it to a contiguous range of tiles (= a contiguous range of mesh
+ * sections of each phase); x and lam are replicated.  pcx_eval then (stage 1)
+ * writes only the value slots those sections own -- disjoint slabs of the
+ * full-size c/dy/jac/hess arrays -- and leaves this rank's share of the few
+ * cross-mesh quantities (quadrature partial sums of the integral rows and of
+ * the t/s blocks of H, end-node Hessian values; nothing like it exists in the
+ * reference, whose CasADi graph is one monolithic function) in a small device
+ * buffer.  The caller all-reduces (sum) that buffer over the ranks (NCCL) and
+ * calls pcx_apply_border (stage 2), which writes the O(1) border slots
+ * (integral/endpoint rows, q/t/s corner, J, gradient entries).              */
+int pcx_set_shard(pcx_engine* e, int tile_begin, int tile_end);
+int pcx_shard_buffer(pcx_engine* e, double** xbuf, int64_t* n);
+int pcx_apply_border(pcx_engine* e, int what, const double* x, const double* lam,
+                     const double* sigma, double* f, double* grad, double* c,
+                     double* jac, double* hess, void* stream);
+
 /* ---- mesh-refinement error -----------------
  * Replaces PattersonRaoMeshRefinement.generate_dy_ph_callables +
  * phase_mesh_error (pycollo/mesh_refinement.py:88-158, 206-240) for an engine

@@ -51,6 +51,7 @@ class _CudaPrinter(C99CodePrinter):
 
 
 _PRINTER = _CudaPrinter()
+_OUTPUTS_LAST = bool(int(__import__('os').environ.get('PCX_CODEGEN_OUTPUTS_LAST', '0')))
 
 
 def _ccode(e):
@@ -138,10 +139,21 @@ def _emit_program(inputs, outputs, indent="        "):
     for s, cexpr in inputs:
         lines.append(f"{indent}const double {s} = {cexpr};")
     lines.extend(pre)
-    for s, e in repl:
-        lines.append(f"{indent}const double {s} = {_ccode(e)};")
+    # every output is emitted right after the last temporary it needs, so a
+    # consumer that stores it at once (the node sink of pcx_kernels.cuh) keeps
+    # no result live across the rest of the program
+    where = {s_: i for i, (s_, _) in enumerate(repl)}
+    after = {}
     for (lv, _), e in zip(outputs, reduced):
-        lines.append(f"{indent}{lv} = {_ccode(e)};")
+        pos = max([where[f] for f in e.free_symbols if f in where], default=-1)
+        if _OUTPUTS_LAST:
+            pos = len(repl) - 1
+        stmt = lv.format(_ccode(e)) if "{}" in lv else f"{lv} = {_ccode(e)};"
+        after.setdefault(pos, []).append(f"{indent}{stmt}")
+    lines.extend(after.get(-1, []))
+    for i, (s, e) in enumerate(repl):
+        lines.append(f"{indent}const double {s} = {_ccode(e)};")
+        lines.extend(after.get(i, []))
     return "\n".join(lines)
 
 
@@ -268,20 +280,20 @@ def _phase_struct(q, ph, pd, lay, NS):
     mut = [sym.Symbol(f"mt{e}") for e in range(NF)]
     outputs = []
     for e, fe in enumerate(pd.fns):
-        outputs.append((f"F[{e}]", fe.xreplace(sub)))
+        outputs.append((f"o.template F<{e}>({{}});", fe.xreplace(sub)))
     for k, de in enumerate(pd.d1v_expr):
-        outputs.append((f"D1V[{k}]", de.xreplace(sub)))
+        outputs.append((f"o.template D1V<{k}>({{}});", de.xreplace(sub)))
     for k, de in enumerate(pd.d1s_expr):
-        outputs.append((f"D1S[{k}]", de.xreplace(sub)))
+        outputs.append((f"o.template D1S<{k}>({{}});", de.xreplace(sub)))
     contr = {}
     for (e, a, b, dab) in pd.d2:
         contr[(a, b)] = contr.get((a, b), 0) + muh[e] * dab.xreplace(sub)
     for k, (a, b) in enumerate(pd.h2vv):
-        outputs.append((f"H2VV[{k}]", contr[(a, b)]))
+        outputs.append((f"o.template H2VV<{k}>({{}});", contr[(a, b)]))
     for k, (a, j) in enumerate(pd.h2vs):
-        outputs.append((f"H2VS[{k}]", contr[(a, NV + j)]))
+        outputs.append((f"o.template H2VS<{k}>({{}});", contr[(a, NV + j)]))
     for k, (i, j) in enumerate(pd.h2ss):
-        outputs.append((f"H2SS[{k}]", contr[(NV + i, NV + j)]))
+        outputs.append((f"o.template H2SS<{k}>({{}});", contr[(NV + i, NV + j)]))
     d1_by_var = {}
     for (e, a), de in zip(pd.d1v, pd.d1v_expr):
         if pd.fam[e] in "di":
@@ -290,19 +302,19 @@ def _phase_struct(q, ph, pd, lay, NS):
         if pd.fam[e] in "di":
             d1_by_var[NV + j] = d1_by_var.get(NV + j, 0) + mut[e] * de.xreplace(sub)
     for k, a in enumerate(pd.htv):
-        outputs.append((f"HTV[{k}]", d1_by_var[a]))
+        outputs.append((f"o.template HTV<{k}>({{}});", d1_by_var[a]))
     for k, j in enumerate(pd.hts):
-        outputs.append((f"HTS[{k}]", d1_by_var[NV + j]))
+        outputs.append((f"o.template HTS<{k}>({{}});", d1_by_var[NV + j]))
     inputs = [(f"v{a}", f"v[{a}]") for a in range(NV + NS)]
     inputs += [(f"mh{e}", f"muh[{e}]") for e in range(NF)]
     inputs += [(f"mt{e}", f"mut[{e}]") for e in range(NF)]
-    s.append("    static __device__ __forceinline__ void eval(\n"
+    # results are handed to a sink (``o.template D1V<k>(value)`` ...) the moment
+    # they exist instead of being returned in arrays: with tens of outputs per
+    # node the arrays alone would not fit the register file
+    s.append("    template <class Sink>\n"
+             "    static __device__ __forceinline__ void eval(\n"
              "        const double* __restrict__ v, const double* __restrict__ muh,\n"
-             "        const double* __restrict__ mut, double* __restrict__ F,\n"
-             "        double* __restrict__ D1V, double* __restrict__ D1S,\n"
-             "        double* __restrict__ H2VV, double* __restrict__ H2VS,\n"
-             "        double* __restrict__ H2SS, double* __restrict__ HTV,\n"
-             "        double* __restrict__ HTS) {\n")
+             "        const double* __restrict__ mut, Sink& o) {\n")
     s.append(_emit_program(inputs, outputs))
     s.append("\n    }\n};\n")
     return "".join(s)

@@ -135,6 +135,101 @@ __host__ __device__ constexpr bool pcx_need_red() {
 }
 
 // ---------------------------------------------------------------------------
+// Destination of the per-node results of the generated body PcxPhase<P>::eval.
+// Every method is a compile-time-indexed store: nothing the body computes stays
+// live after it has been produced (a problem like the Delta III launcher has
+// ~90 results per node; held in arrays they alone overflow the register file).
+// ---------------------------------------------------------------------------
+template <class Ph>
+struct PcxNodeSink {
+    static constexpr int F_ = PCX_FLAGS;
+    static constexpr bool WANT_C = (F_ & PCX_F_C) != 0, WANT_DY = (F_ & PCX_F_DY) != 0;
+    static constexpr bool WANT_G = (F_ & PCX_F_G) != 0, WANT_H = (F_ & PCX_F_H) != 0;
+    static constexpr bool HAS_T = Ph::HAS_T0 || Ph::HAS_TF;
+    static constexpr bool NEED_SF = WANT_C || (WANT_G && HAS_T);
+    static constexpr int NY = Ph::NY, NP = Ph::NP;
+
+    const double* ps; const i64* pb;
+    double *sF, *sD, *sDS, *sDP;          // already offset by the node / section
+    int nnp, nsp;
+    bool sec_start, owned, regular;
+    double hp, wq, h_k, h_pr;
+    i64 m, N;
+    double *out_c_path, *out_dy, *out_g, *out_h, *irr, *red;
+
+    // rank of first-derivative-by-parameter entry K among those of one family
+    static __host__ __device__ constexpr int d1s_rank(int K, int fam) {
+        int c = 0;
+        for (int k = 0; k < K; ++k) if (Ph::FAM(Ph::D1S_FN(k)) == fam) ++c;
+        return c;
+    }
+
+    template <int I> __device__ __forceinline__ void F(const double val) const {
+        if (I < NY) {
+            if (NEED_SF) sF[I * nnp] = val;
+            if (WANT_DY && owned) out_dy[(i64)I * N] = val;
+        } else if (I < NY + NP) {
+            if (WANT_C && owned)
+                out_c_path[(i64)(I - NY) * N] = ps[Ph::OFF_WFN + I] * val;
+        } else {
+            if ((WANT_C || (WANT_G && HAS_T)) && owned)
+                red[Ph::RED_G + (I - NY - NP)] += wq * val;
+        }
+    }
+    // defect-family entries are staged already multiplied by the length of the
+    // section that owns the row: h_k for rows of the node's own section and, at
+    // a section's first node, h_{k-1} for the rows of the previous section
+    // (second copy, one slot per section)
+    template <int K> __device__ __forceinline__ void D1V(const double val) const {
+        if (!WANT_G) return;
+        constexpr int fam = Ph::FAM(Ph::D1V_FN(K));
+        const double fac = fam == 0 ? hp : (fam == 1 ? 1.0 : -hp * wq);
+        const double d = ps[Ph::OFF_D1V + K] * fac * val;
+        sD[K * nnp] = fam == 0 ? d * h_k : d;
+        if (fam == 0 && sec_start) sDP[K * nsp] = d * h_pr;
+    }
+    template <int K> __device__ __forceinline__ void D1S(const double val) const {
+        if (!WANT_G) return;
+        constexpr int fam = Ph::FAM(Ph::D1S_FN(K));
+        if (fam == 0) {
+            sDS[d1s_rank(K, 0) * nnp] = ps[Ph::OFF_D1S + K] * hp * val;
+        } else if (fam == 1) {
+            if (owned) out_g[pb[Ph::PB_GSCOL + K] + m] = ps[Ph::OFF_D1S + K] * val;
+        } else {
+            if (owned) red[Ph::RED_GS + d1s_rank(K, 2)] += wq * val;
+        }
+    }
+    template <int K> __device__ __forceinline__ void H2VV(const double val) const {
+        if (!WANT_H || !owned) return;
+        if (regular)
+            out_h[pb[Ph::PB_HREG + Ph::H2VV_B(K)] + (m - 1) * Ph::NA(Ph::H2VV_B(K))
+                  + Ph::H2VV_POS(K)] = ps[Ph::OFF_H2VV + K] * val;
+        else
+            irr[K] = val;
+    }
+    template <int K> __device__ __forceinline__ void H2VS(const double val) const {
+        if (!WANT_H || !owned) return;
+        if (regular) out_h[pb[Ph::PB_HS + K] + (m - 1)] = ps[Ph::OFF_H2VS + K] * val;
+        else irr[Ph::NH2VV + K] = val;
+    }
+    template <int K> __device__ __forceinline__ void HTV(const double val) const {
+        if (!WANT_H || !owned) return;
+        if (regular) {
+            if (Ph::HAS_T0) out_h[pb[Ph::PB_HT0 + K] + (m - 1)] = ps[Ph::OFF_HT0 + K] * val;
+            if (Ph::HAS_TF) out_h[pb[Ph::PB_HTF + K] + (m - 1)] = ps[Ph::OFF_HTF + K] * val;
+        } else {
+            irr[Ph::NH2VV + Ph::NH2VS + K] = val;
+        }
+    }
+    template <int K> __device__ __forceinline__ void HTS(const double val) const {
+        if (WANT_H && owned) red[Ph::RED_HTS + K] += val;
+    }
+    template <int K> __device__ __forceinline__ void H2SS(const double val) const {
+        if (WANT_H && owned) red[Ph::RED_HSS + K] += val;
+    }
+};
+
+// ---------------------------------------------------------------------------
 // One tile of phase Ph.  A tile that writes something the border pass reads
 // (reduction partials, end-node values) or overwrites (gradient zeros) fences
 // those writes and bumps the instance's ticket as soon as its node phase ends.
@@ -357,91 +452,21 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
             }
         }
 
-        PcxArr<NF> Fv; PcxArr<Ph::ND1V> D1V; PcxArr<Ph::ND1S> D1S;
-        PcxArr<Ph::NH2VV> H2VV; PcxArr<Ph::NH2VS> H2VS; PcxArr<Ph::NH2SS> H2SS;
-        PcxArr<Ph::NHTV> HTV; PcxArr<Ph::NHTS> HTS;
-        Ph::eval(v, muh, mut, Fv.v, D1V.v, D1S.v, H2VV.v, H2VS.v, H2SS.v, HTV.v, HTS.v);
-
-        if (NEED_SF) {
-#pragma unroll
-            for (int i = 0; i < NY; ++i) sF[i * nnp + ml] = Fv.v[i];
-        }
-        if (WANT_DY && owned) {
-#pragma unroll
-            for (int i = 0; i < NY; ++i)
-                out_dy[pb[Ph::PB_DYOFF] + (i64)i * N + m] = Fv.v[i];
-        }
-        if (WANT_C && owned) {
-#pragma unroll
-            for (int j = 0; j < NP; ++j)
-                out_c[co + (i64)NY * (N - 1) + (i64)j * N + m] =
-                    ps[Ph::OFF_WFN + NY + j] * Fv.v[NY + j];
-        }
-        if ((WANT_C || (WANT_G && HAS_T)) && owned) {
-#pragma unroll
-            for (int i = 0; i < NQ; ++i) red[Ph::RED_G + i] += wq * Fv.v[NY + NP + i];
-        }
-        if (WANT_G) {
-#pragma unroll
-            // defect-family entries are staged already multiplied by the length
-            // of the section that owns the row: h_k for rows of the node's own
-            // section and, at a section's first node, h_{k-1} for the rows of
-            // the previous section (second copy, one slot per section)
-            for (int k = 0; k < Ph::ND1V; ++k) {
-                const int fam = Ph::FAM(Ph::D1V_FN(k));
-                const double fac = fam == 0 ? hp : (fam == 1 ? 1.0 : -hp * wq);
-                const double d = ps[Ph::OFF_D1V + k] * fac * D1V.v[k];
-                sD[k * nnp + ml] = fam == 0 ? d * h_k : d;
-                if (fam == 0 && mloc == 0) sDP[k * nsp + s] = d * h_pr;
-            }
-            int kd = 0, kr = 0;
-#pragma unroll
-            for (int k = 0; k < Ph::ND1S; ++k) {
-                const int fam = Ph::FAM(Ph::D1S_FN(k));
-                if (fam == 0) {
-                    sDS[kd * nnp + ml] = ps[Ph::OFF_D1S + k] * hp * D1S.v[k];
-                    ++kd;
-                } else if (fam == 1) {
-                    if (owned) out_g[pb[Ph::PB_GSCOL + k] + m] =
-                        ps[Ph::OFF_D1S + k] * D1S.v[k];
-                } else {
-                    if (owned) red[Ph::RED_GS + kr] += wq * D1S.v[k];
-                    ++kr;
-                }
-            }
-        }
-        if (WANT_H && owned) {
-            const bool irregular = (m == 0) || (m == N - 1);
-            if (!irregular) {
-#pragma unroll
-                for (int k = 0; k < Ph::NH2VV; ++k)
-                    out_h[pb[Ph::PB_HREG + Ph::H2VV_B(k)]
-                          + (m - 1) * Ph::NA(Ph::H2VV_B(k)) + Ph::H2VV_POS(k)] =
-                        ps[Ph::OFF_H2VV + k] * H2VV.v[k];
-#pragma unroll
-                for (int k = 0; k < Ph::NH2VS; ++k)
-                    out_h[pb[Ph::PB_HS + k] + (m - 1)] = ps[Ph::OFF_H2VS + k] * H2VS.v[k];
-#pragma unroll
-                for (int k = 0; k < Ph::NHTV; ++k) {
-                    if (Ph::HAS_T0)
-                        out_h[pb[Ph::PB_HT0 + k] + (m - 1)] = ps[Ph::OFF_HT0 + k] * HTV.v[k];
-                    if (Ph::HAS_TF)
-                        out_h[pb[Ph::PB_HTF + k] + (m - 1)] = ps[Ph::OFF_HTF + k] * HTV.v[k];
-                }
-            } else {
-                double* irr = bv + pb[m == 0 ? Ph::PB_IRR0 : Ph::PB_IRR1];
-#pragma unroll
-                for (int k = 0; k < Ph::NH2VV; ++k) irr[k] = H2VV.v[k];
-#pragma unroll
-                for (int k = 0; k < Ph::NH2VS; ++k) irr[Ph::NH2VV + k] = H2VS.v[k];
-#pragma unroll
-                for (int k = 0; k < Ph::NHTV; ++k) irr[Ph::NH2VV + Ph::NH2VS + k] = HTV.v[k];
-            }
-#pragma unroll
-            for (int k = 0; k < Ph::NHTS; ++k) red[Ph::RED_HTS + k] += HTS.v[k];
-#pragma unroll
-            for (int k = 0; k < Ph::NH2SS; ++k) red[Ph::RED_HSS + k] += H2SS.v[k];
-        }
+        // the generated body hands every result to the sink the moment it
+        // exists: staged (G), stored (H, dy, path rows of c) or accumulated
+        PcxNodeSink<Ph> sink;
+        sink.ps = ps; sink.pb = pb;
+        sink.sF = sF + ml; sink.sD = sD + ml; sink.sDS = sDS + ml; sink.sDP = sDP + s;
+        sink.nnp = nnp; sink.nsp = nsp; sink.sec_start = (mloc == 0);
+        sink.hp = hp; sink.wq = wq; sink.h_k = h_k; sink.h_pr = h_pr;
+        sink.owned = owned; sink.regular = (m != 0) && (m != N - 1);
+        sink.m = m; sink.N = N;
+        sink.out_c_path = WANT_C ? out_c + co + (i64)NY * (N - 1) + m : nullptr;
+        sink.out_dy = WANT_DY ? out_dy + pb[Ph::PB_DYOFF] + m : nullptr;
+        sink.out_g = out_g; sink.out_h = out_h;
+        sink.irr = bv + pb[m == 0 ? Ph::PB_IRR0 : Ph::PB_IRR1];
+        sink.red = red;
+        Ph::eval(v, muh, mut, sink);
         if (WANT_GRAD && owned) {
 #pragma unroll
             for (int a = 0; a < NV; ++a) out_grad[xo + (i64)a * N + m] = 0.0;
@@ -610,12 +635,20 @@ __device__ __forceinline__ u32 pcx_ld_acquire(const u32* ptr) {
     return v;
 }
 
-// tiles of phase q that signal the ticket for this output selection
+// tiles of phase q = [a, b) inside this engine's range [B, E) that signal the
+// ticket for this output selection
 template <class Ph>
-__device__ __forceinline__ int pcx_signalling_tiles(int nt) {
+__device__ __forceinline__ int pcx_signalling_tiles(int a, int b, int B, int E) {
     constexpr int F = PCX_FLAGS;
-    if (pcx_need_red<Ph>()) return nt;
-    if ((F & PCX_F_H) || (F & PCX_F_GRAD)) return nt < 2 ? nt : 2;
+    if (pcx_need_red<Ph>()) {
+        const int lo = a > B ? a : B, hi = b < E ? b : E;
+        return hi > lo ? hi - lo : 0;
+    }
+    if ((F & PCX_F_H) || (F & PCX_F_GRAD)) {
+        int n = (a >= B && a < E) ? 1 : 0;
+        if (b - 1 != a && b - 1 >= B && b - 1 < E) ++n;
+        return n;
+    }
     return 0;
 }
 
@@ -693,13 +726,28 @@ __device__ void pcx_border(const PcxParams& p, const int inst, double* scratch)
     if (tid == 0)
         pcx_point_eval(sPt, sMult, bv + PCX_BV_PTFN, bv + PCX_BV_PTD1, bv + PCX_BV_PTD2);
     __syncthreads();
-    pcx_border_map(p, inst, bv, sRS, false, scratch + 31);   // warm the map tables
+    const int mode = p.border_mode;
+    const int xlen = (PCX_BV_PTVAL - 1) + (p.bv_size - PCX_BV_IRR);
+    double* xb = p.xbuf + (i64)inst * xlen;
+    if (mode != 1) pcx_border_map(p, inst, bv, sRS, false, scratch + 31);   // warm the map tables
+
+    if (mode == 2) {
+        // stage 2 of a sharded evaluation: reductions and end-node values come
+        // all-reduced over the ranks
+        for (int i = 1 + tid; i < PCX_BV_PTVAL; i += T) bv[i] = xb[i - 1];
+        for (int i = PCX_BV_IRR + tid; i < p.bv_size; i += T)
+            bv[i] = xb[(PCX_BV_PTVAL - 1) + (i - PCX_BV_IRR)];
+        __syncthreads();
+        pcx_border_map(p, inst, bv, sRS, true, nullptr);
+        return;
+    }
 
     // ---- wait for the tiles that feed the border ------------------------------
+    const int tB = p.tile_begin, tE = p.tile_begin + p.tile_count;
     int expected = 0;
 #define PCX_CASE(P) expected += pcx_signalling_tiles<PcxPhase<P> >(                      \
-        (int)(pcx_c_pbase[PCX_PHASE_PBASE(P) + PCX_PB_TILE1]                             \
-              - pcx_c_pbase[PCX_PHASE_PBASE(P) + PCX_PB_TILE0]));
+        (int)pcx_c_pbase[PCX_PHASE_PBASE(P) + PCX_PB_TILE0],                             \
+        (int)pcx_c_pbase[PCX_PHASE_PBASE(P) + PCX_PB_TILE1], tB, tE);
     PCX_FOREACH_PHASE(PCX_CASE)
 #undef PCX_CASE
     if (expected > 0) {
@@ -720,7 +768,9 @@ __device__ void pcx_border(const PcxParams& p, const int inst, double* scratch)
 #undef PCX_CASE
         const int nred = need ? PCX_PHASE_NRED(q) : 0;
         const i64* pbq = pcx_c_pbase + PCX_PHASE_PBASE(q);
-        const int t_lo = (int)pbq[PCX_PB_TILE0], t_hi = (int)pbq[PCX_PB_TILE1];
+        int t_lo = (int)pbq[PCX_PB_TILE0], t_hi = (int)pbq[PCX_PB_TILE1];
+        if (t_lo < tB) t_lo = tB;
+        if (t_hi > tE) t_hi = tE;
         for (int k = 0; k < nred; ++k) {
             double acc = 0.0;
             for (int t = t_lo + tid; t < t_hi; t += T)
@@ -730,7 +780,14 @@ __device__ void pcx_border(const PcxParams& p, const int inst, double* scratch)
         }
     }
     __syncthreads();
-    pcx_border_map(p, inst, bv, sRS, true, nullptr);
+    if (mode == 1) {
+        // stage 1 of a sharded evaluation: publish this rank's share
+        for (int i = 1 + tid; i < PCX_BV_PTVAL; i += T) xb[i - 1] = bv[i];
+        for (int i = PCX_BV_IRR + tid; i < p.bv_size; i += T)
+            xb[(PCX_BV_PTVAL - 1) + (i - PCX_BV_IRR)] = bv[i];
+    } else {
+        pcx_border_map(p, inst, bv, sRS, true, nullptr);
+    }
     if (tid == 0) p.ticket[inst] = 0u;
 }
 
@@ -743,7 +800,7 @@ PCX_KERNEL_NAME(const PcxParams p)
     // its own instance could use
     int tile = p.border_first ? (int)blockIdx.x - 1 : (int)blockIdx.x;
     const int inst = blockIdx.y;
-    if (tile == (p.border_first ? -1 : p.num_tiles)) {
+    if (tile == (p.border_first ? -1 : p.tile_count)) {
 #ifndef PCX_DEBUG_NO_BORDER
         pcx_border(p, inst, reinterpret_cast<double*>(pcx_smem));
         PCX_STAMP_B(6);
@@ -754,11 +811,12 @@ PCX_KERNEL_NAME(const PcxParams p)
     // memory tile ranges, without a dependent global load.  The last tile of a
     // phase trades places with the second one, so that both tiles the border
     // pass may wait for (first and last: end-node values) are dispatched first.
+    tile += p.tile_begin;
     int phase = 0;
 #pragma unroll
     for (int q = 1; q < PCX_NUM_PHASES; ++q)
         if (tile >= (int)pcx_c_pbase[PCX_PHASE_PBASE(q) + PCX_PB_TILE0]) phase = q;
-    {
+    if (p.border_mode == 0) {
         const int t_lo = (int)pcx_c_pbase[PCX_PHASE_PBASE(phase) + PCX_PB_TILE0];
         const int t_hi = (int)pcx_c_pbase[PCX_PHASE_PBASE(phase) + PCX_PB_TILE1];
         if (t_hi - t_lo > 2) {

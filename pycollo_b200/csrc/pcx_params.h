@@ -39,6 +39,12 @@ struct PcxParams {
     i64 num_x, num_c, num_dy, nnz_g, nnz_h;
     int num_tiles, batch, nvmax, n_border, bv_size, nred_max, btab_len;
     int border_first;       // 1: the border CTA is blockIdx.x == 0 (resident from the start)
+    // mesh sharding over GPUs (pcx_set_shard): this engine launches tiles
+    // [tile_begin, tile_begin + tile_count) only.  border_mode 0: whole mesh on
+    // one GPU; 1: local reductions / end-node values -> xbuf, no border map
+    // (stage 1); 2: border CTA only, reads the all-reduced xbuf (stage 2)
+    int tile_begin, tile_count, border_mode;
+    double* xbuf;           // (batch, xbuf_len): [reductions | end-node values]
     // tiles
     const i64* tile_desc;   // 8 per tile: phase,k0,k1,node0,nn,run0,run1,-
     const int* run_slo; const int* run_shi; const int* run_type;

@@ -85,6 +85,9 @@ def load_library(rebuild=False):
     lib.pcx_launch_count.restype = i64
     lib.pcx_synchronize.argtypes = [vp, vp]
     lib.pcx_flush_l2.argtypes = [vp, i64, vp]
+    lib.pcx_set_shard.argtypes = [vp, i32, i32]
+    lib.pcx_shard_buffer.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
+    lib.pcx_apply_border.argtypes = [vp, i32, dp, dp, dp, dp, dp, dp, dp, dp, vp]
     lib.pcx_mesh_error.argtypes = [vp, dp, dp, dp, dp, i32, vp]
     lib.pcx_mesh_error_sizes.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     _LIB = lib
@@ -338,6 +341,25 @@ class Engine:
             _ptr(out.get("grad")), _ptr(out.get("c")), _ptr(out.get("dy")),
             _ptr(out.get("jac")), _ptr(out.get("hess")), PCX_HOST, None), "pcx_eval")
         return out
+
+    # -- one mesh over several GPUs (include/pcx.h) ----
+    def set_shard(self, tile_begin, tile_end):
+        self._check(self.lib.pcx_set_shard(self.h, int(tile_begin), int(tile_end)),
+                    "pcx_set_shard")
+
+    def shard_buffer(self):
+        """(device pointer, length) of the small border-exchange buffer."""
+        ptr, n = ctypes.c_void_p(), ctypes.c_int64()
+        self._check(self.lib.pcx_shard_buffer(self.h, ctypes.byref(ptr), ctypes.byref(n)),
+                    "pcx_shard_buffer")
+        return int(ptr.value), int(n.value)
+
+    def apply_border(self, what, x, lam=None, sigma=None, f=None, grad=None, c=None,
+                     jac=None, hess=None, stream=None):
+        self._check(self.lib.pcx_apply_border(
+            self.h, what, _ptr(x), _ptr(lam), _ptr(sigma), _ptr(f), _ptr(grad), _ptr(c),
+            _ptr(jac), _ptr(hess), ctypes.c_void_p(stream) if stream else None),
+            "pcx_apply_border")
 
     def mesh_error_sizes(self):
         ne, ns = ctypes.c_int64(), ctypes.c_int64()

@@ -9,10 +9,12 @@ values is one ``all_gather`` issued over NCCL/NVLink (or gloo on CPU tensors in
 the tests).
 
 Splitting ONE very large mesh over GPUs (BASELINE config 4) is the other natural
-partition -- contiguous tile ranges per rank, an ``all_reduce`` of the few
-integral/border partial sums and an ``all_gather`` of value slabs; the tile
-tables already support it (tiles are independent, ``tile_desc``), the border
-pass split it needs is listed under "next" in DESIGN.md.
+partition (``MeshSharder``): every rank builds the same engine, restricts it to
+a contiguous range of tiles (``pcx_set_shard``), evaluates its slabs of the
+value arrays, and the only exchange is one NCCL ``all_reduce`` of a few dozen
+doubles -- the quadrature partial sums and end-node values the border slots
+need -- between the two stages of the border pass.  x and lam are replicated
+(each rank reads them from its own pinned host buffer or a broadcast).
 """
 from __future__ import annotations
 
@@ -82,3 +84,53 @@ class InstanceSharder:
         self.dist.all_gather(out, buf)
         full = torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0)
         return full.cpu().numpy()
+
+
+class _DeviceArray:
+    """CUDA-array-interface view of a raw device pointer (for torch.as_tensor)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = dict(shape=(int(n),), typestr="<f8",
+                                             data=(int(ptr), False), version=2)
+
+
+class MeshSharder:
+    """One mesh split over the ranks by contiguous tile ranges (config 4).
+
+    ``evaluate`` = stage 1 (this rank's tiles; its slab of every selected value
+    array, slots disjoint between ranks) -> ``all_reduce(sum)`` of the border
+    exchange buffer over NCCL -> stage 2 (border slots).  With ``border_rank``
+    set, only that rank writes the O(1) border slots, so that a sum over ranks of
+    zero-initialised arrays reassembles the full vectors exactly (each slot has
+    exactly one writer); with ``border_rank=None`` every rank writes them.
+    """
+
+    def __init__(self, engine, world_size=None, rank=None, border_rank=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        if world_size is None:
+            world_size = dist.get_world_size() if dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world_size, self.rank = int(world_size), int(rank)
+        self.engine = engine
+        self.border_rank = border_rank
+        self.lo, self.hi = shard_range(engine.S.num_tiles, self.world_size, self.rank)
+        engine.set_shard(self.lo, self.hi)
+        ptr, n = engine.shard_buffer()
+        self.xbuf = torch.as_tensor(_DeviceArray(ptr, n), device=f"cuda:{engine.device}")
+
+    def evaluate(self, what, x, lam=None, sigma=None, f=None, grad=None, c=None, dy=None,
+                 jac=None, hess=None):
+        """Device tensors in, device tensors (full-size, this rank's slab filled) out;
+        everything is enqueued on torch's current stream."""
+        st = self.torch.cuda.current_stream().cuda_stream
+        self.engine.eval_ptr(what, x, lam=lam, sigma=sigma, f=f, grad=grad, c=c, dy=dy,
+                             jac=jac, hess=hess, stream=st)
+        if self.world_size == 1:
+            return                       # unsharded engine: pcx_eval did the border pass
+        self.dist.all_reduce(self.xbuf)
+        if self.border_rank is None or self.border_rank == self.rank:
+            self.engine.apply_border(what, x, lam=lam, sigma=sigma, f=f, grad=grad, c=c,
+                                     jac=jac, hess=hess, stream=st)

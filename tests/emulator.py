@@ -69,7 +69,12 @@ def _point_fn(ptd, NB):
     return call
 
 
-def emulate(low, tables, scal, x, lam=None, sigma=1.0, flags=F_G | F_H):
+def emulate(low, tables, scal, x, lam=None, sigma=1.0, flags=F_G | F_H,
+            tile_range=None, stage=0, xbuf=None):
+    """stage 0: whole evaluation.  Sharded (pcx_set_shard / pcx_apply_border):
+    stage 1 walks ``tile_range`` only and returns this rank's border share in
+    ``out["xbuf"]`` instead of applying the border map; stage 2 walks no tile and
+    applies the border map from the (all-reduced) ``xbuf``."""
     S, layouts = low.S, low.layouts
     pscal, gscal, bcoef, pt_scal = scal
     T = tables
@@ -84,7 +89,8 @@ def emulate(low, tables, scal, x, lam=None, sigma=1.0, flags=F_G | F_H):
     partials = np.zeros((S.num_tiles, nred_max))
     sB = T["btab"]
     sec_node_all = T["sec_node"]
-    for tile in range(S.num_tiles):
+    tB, tE = (0, S.num_tiles) if tile_range is None else tile_range
+    for tile in (range(tB, tE) if stage != 2 else ()):
         td = T["tile_desc"].reshape(-1, 8)[tile]
         q = int(td[0])
         lay, pd = layouts[q], layouts[q].pd
@@ -281,8 +287,16 @@ def emulate(low, tables, scal, x, lam=None, sigma=1.0, flags=F_G | F_H):
     for q, lay in enumerate(layouts):
         pb = T["pbase"][lay.pbase_off:lay.pbase_off + lay.pbase_size]
         t_lo, t_hi = int(pb[lay.pb["TILE0"]]), int(pb[lay.pb["TILE1"]])
+        t_lo, t_hi = max(t_lo, tB), min(t_hi, tE)
         for k in range(lay.nred):
-            bv[S.ph[q].red_off + k] = partials[t_lo:t_hi, k].sum()
+            bv[S.ph[q].red_off + k] = partials[t_lo:t_hi, k].sum() if t_hi > t_lo else 0.0
+    if stage == 1:
+        out["xbuf"] = np.concatenate([bv[1:S.bv_ptval], bv[S.bv_irr0:]])
+        return out
+    if stage == 2:
+        nr = S.bv_ptval - 1
+        bv[1:S.bv_ptval] = xbuf[:nr]
+        bv[S.bv_irr0:] = xbuf[nr:nr + S.bv_size - S.bv_irr0]
     npt = len(low.ptd.pts)
     pt = [pt_scal[a] * x[T["pt_x"][a]] + pt_scal[npt + a] for a in range(npt)]
     bv[S.bv_ptval:S.bv_ptval + npt] = pt
