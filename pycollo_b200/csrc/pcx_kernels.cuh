@@ -678,7 +678,8 @@ __device__ void pcx_border_map(const PcxParams& p, const int inst, const double*
     if (!commit) *sink_slot = sink;
 }
 
-__device__ void pcx_border(const PcxParams& p, const int inst, double* scratch)
+__device__ __noinline__ void pcx_border(const PcxParams& p, const int inst, double* scratch,
+                                        const bool wait_for_tiles = true)
 {
     constexpr int F = PCX_FLAGS;
     constexpr int T = PCX_THREADS;
@@ -750,7 +751,7 @@ __device__ void pcx_border(const PcxParams& p, const int inst, double* scratch)
         (int)pcx_c_pbase[PCX_PHASE_PBASE(P) + PCX_PB_TILE1], tB, tE);
     PCX_FOREACH_PHASE(PCX_CASE)
 #undef PCX_CASE
-    if (expected > 0) {
+    if (expected > 0 && wait_for_tiles) {
         if (tid == 0) {
             while (pcx_ld_acquire(p.ticket + inst) < (u32)expected) __nanosleep(64);
         }
@@ -792,7 +793,7 @@ __device__ void pcx_border(const PcxParams& p, const int inst, double* scratch)
 }
 
 extern "C" __global__ void __launch_bounds__(PCX_THREADS, PCX_MIN_BLOCKS)
-PCX_KERNEL_NAME(const PcxParams p)
+PCX_KERNEL_NAME(const __grid_constant__ PcxParams p)
 {
     extern __shared__ __align__(16) unsigned char pcx_smem[];
     // large meshes: the border CTA is dispatched first and works in the shadow
@@ -800,7 +801,11 @@ PCX_KERNEL_NAME(const PcxParams p)
     // its own instance could use
     int tile = p.border_first ? (int)blockIdx.x - 1 : (int)blockIdx.x;
     const int inst = blockIdx.y;
-    if (tile == (p.border_first ? -1 : p.tile_count)) {
+    // multi-start sweeps of small problems (one tile per instance): the tile's
+    // own CTA runs the border pass afterwards -- no second CTA, no ticket wait
+    const bool solo = (p.num_tiles == 1 && p.border_mode == 0);
+    if (solo) tile = 0;
+    if (!solo && tile == (p.border_first ? -1 : p.tile_count)) {
 #ifndef PCX_DEBUG_NO_BORDER
         pcx_border(p, inst, reinterpret_cast<double*>(pcx_smem));
         PCX_STAMP_B(6);
@@ -831,4 +836,9 @@ PCX_KERNEL_NAME(const PcxParams p)
         default: break;
     }
     PCX_STAMP(5);
+    if (solo) {
+        __threadfence();
+        __syncthreads();
+        pcx_border(p, inst, reinterpret_cast<double*>(pcx_smem), false);
+    }
 }

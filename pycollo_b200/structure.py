@@ -128,13 +128,18 @@ class PhaseTables:
 
 class NLPStructure:
     def __init__(self, ir, phase_derivs, point_derivs, meshes, *, prune=True,
-                 sm_count=148, threads=128, max_tile_nodes=None,
+                 sm_count=148, threads=None, max_tile_nodes=None,
                  smem_budget=96 * 1024, tiles_per_sm=None):
         self.ir = ir
         self.pd = phase_derivs
         self.pt = point_derivs
         self.meshes = meshes
         self.prune = bool(prune)
+        if threads is None:
+            # CTA size: one thread per node of a tile; small problems (multi-start
+            # sweeps of ~31-node meshes) get a CTA no wider than their mesh
+            nmax = max(int(m.N) for m in meshes)
+            threads = 32 if nmax <= 32 else (64 if nmax <= 64 else 128)
         self.threads = int(threads)
         self.P = len(ir.phases)
         self.NS = ir.n_s

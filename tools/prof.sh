@@ -12,3 +12,6 @@ ncu -i $O/prof_$TAG.ncu-rep --page raw --csv > $O/raw_$TAG.csv 2>/dev/null
 ncu -i $O/prof_$TAG.ncu-rep --page source --print-source cuda,sass --csv > $O/src_$TAG.csv 2>/dev/null
 ls -la $O/prof_$TAG.ncu-rep
 rm -f pcx_kernels.cu pcx_problem.h pcx_params.h
+# launch list of the same command (per-launch durations, cold-cache and serialised)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv \
+    python bench.py --steps 30 --warmup 5 --no-cpu-baseline > $O/ncu_launch_$TAG.log 2>&1
