@@ -229,6 +229,41 @@ struct PcxNodeSink {
     }
 };
 
+// Small expression bodies (a few dozen results per node) fit the register file:
+// there it is cheaper to let the body finish first and only then form the
+// destinations, so the results are parked in registers by this sink and handed
+// to the real one afterwards.
+template <class Ph>
+struct PcxParkingSink {
+    double f[Ph::NF > 0 ? Ph::NF : 1], d1v[Ph::ND1V > 0 ? Ph::ND1V : 1];
+    double d1s[Ph::ND1S > 0 ? Ph::ND1S : 1], h2vv[Ph::NH2VV > 0 ? Ph::NH2VV : 1];
+    double h2vs[Ph::NH2VS > 0 ? Ph::NH2VS : 1], h2ss[Ph::NH2SS > 0 ? Ph::NH2SS : 1];
+    double htv[Ph::NHTV > 0 ? Ph::NHTV : 1], hts[Ph::NHTS > 0 ? Ph::NHTS : 1];
+    template <int I> __device__ __forceinline__ void F(const double v) { f[I] = v; }
+    template <int K> __device__ __forceinline__ void D1V(const double v) { d1v[K] = v; }
+    template <int K> __device__ __forceinline__ void D1S(const double v) { d1s[K] = v; }
+    template <int K> __device__ __forceinline__ void H2VV(const double v) { h2vv[K] = v; }
+    template <int K> __device__ __forceinline__ void H2VS(const double v) { h2vs[K] = v; }
+    template <int K> __device__ __forceinline__ void H2SS(const double v) { h2ss[K] = v; }
+    template <int K> __device__ __forceinline__ void HTV(const double v) { htv[K] = v; }
+    template <int K> __device__ __forceinline__ void HTS(const double v) { hts[K] = v; }
+};
+
+template <int... Is> struct PcxSeq {};
+template <int N, int... Is> struct PcxMakeSeq : PcxMakeSeq<N - 1, N - 1, Is...> {};
+template <int... Is> struct PcxMakeSeq<0, Is...> { typedef PcxSeq<Is...> type; };
+
+#define PCX_DRAIN(NAME, FIELD)                                                            \
+    template <class Ph, int... Is>                                                        \
+    __device__ __forceinline__ void pcx_drain_##NAME(const PcxParkingSink<Ph>& a,         \
+                                                     const PcxNodeSink<Ph>& o, PcxSeq<Is...>) { \
+        int dummy[] = {0, (o.template NAME<Is>(a.FIELD[Is]), 0)...};                      \
+        (void)dummy;                                                                      \
+    }
+PCX_DRAIN(F, f) PCX_DRAIN(D1V, d1v) PCX_DRAIN(D1S, d1s) PCX_DRAIN(H2VV, h2vv)
+PCX_DRAIN(H2VS, h2vs) PCX_DRAIN(H2SS, h2ss) PCX_DRAIN(HTV, htv) PCX_DRAIN(HTS, hts)
+#undef PCX_DRAIN
+
 // ---------------------------------------------------------------------------
 // One tile of phase Ph.  A tile that writes something the border pass reads
 // (reduction partials, end-node values) or overwrites (gradient zeros) fences
@@ -454,6 +489,11 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
 
         // the generated body hands every result to the sink the moment it
         // exists: staged (G), stored (H, dy, path rows of c) or accumulated
+        constexpr int NOUT = NF + Ph::ND1V + Ph::ND1S + Ph::NH2VV + Ph::NH2VS + Ph::NH2SS
+                             + Ph::NHTV + Ph::NHTS;
+        constexpr bool PARK = NOUT <= 40;
+        PcxParkingSink<Ph> parked;
+        if (PARK) Ph::eval(v, muh, mut, parked);
         PcxNodeSink<Ph> sink;
         sink.ps = ps; sink.pb = pb;
         sink.sF = sF + ml; sink.sD = sD + ml; sink.sDS = sDS + ml; sink.sDP = sDP + s;
@@ -466,7 +506,18 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         sink.out_g = out_g; sink.out_h = out_h;
         sink.irr = bv + pb[m == 0 ? Ph::PB_IRR0 : Ph::PB_IRR1];
         sink.red = red;
-        Ph::eval(v, muh, mut, sink);
+        if (PARK) {
+            pcx_drain_F(parked, sink, typename PcxMakeSeq<NF>::type());
+            pcx_drain_D1V(parked, sink, typename PcxMakeSeq<Ph::ND1V>::type());
+            pcx_drain_D1S(parked, sink, typename PcxMakeSeq<Ph::ND1S>::type());
+            pcx_drain_H2VV(parked, sink, typename PcxMakeSeq<Ph::NH2VV>::type());
+            pcx_drain_H2VS(parked, sink, typename PcxMakeSeq<Ph::NH2VS>::type());
+            pcx_drain_H2SS(parked, sink, typename PcxMakeSeq<Ph::NH2SS>::type());
+            pcx_drain_HTV(parked, sink, typename PcxMakeSeq<Ph::NHTV>::type());
+            pcx_drain_HTS(parked, sink, typename PcxMakeSeq<Ph::NHTS>::type());
+        } else {
+            Ph::eval(v, muh, mut, sink);
+        }
         if (WANT_GRAD && owned) {
 #pragma unroll
             for (int a = 0; a < NV; ++a) out_grad[xo + (i64)a * N + m] = 0.0;
