@@ -42,6 +42,19 @@ __constant__ double pcx_c_pscal[PCX_PSCAL_TOTAL > 0 ? PCX_PSCAL_TOTAL : 1];
 __constant__ double pcx_c_gscal[PCX_GSCAL_TOTAL > 0 ? PCX_GSCAL_TOTAL : 1];
 __constant__ long long pcx_c_pbase[PCX_PBASE_TOTAL > 0 ? PCX_PBASE_TOTAL : 1];
 
+// Programmatic dependent launch (griddepcontrol, sm_90+): when the host launches
+// with programmatic stream serialisation, the CTAs of this kernel may become
+// resident and run their table-only prologue while the previous kernel in the
+// stream drains; pcx_grid_dependency_wait() returns once that kernel has
+// completed and its writes are visible.  Without the launch attribute both are
+// no-ops.
+__device__ __forceinline__ void pcx_grid_dependency_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pcx_grid_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ double pcx_warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -356,6 +369,10 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     // everything below depends only on the tile descriptor: all global loads of
     // the prologue (this thread's node variables, quadrature table, section
     // table, multipliers) are in flight together before the first barrier
+    // programmatic dependent launch: everything above touched only the engine's
+    // immutable tables; the iterate, the multipliers and every output may belong
+    // to the previous kernel in the stream, which has to be complete from here on
+    pcx_grid_dependency_wait();
     double xt0[NV > 0 ? NV : 1];
 #pragma unroll
     for (int a = 0; a < NV; ++a)
@@ -743,6 +760,7 @@ __device__ __noinline__ void pcx_border(const PcxParams& p, const int inst, doub
     // the border-value vector lives in shared memory for the whole pass
     double* bv = scratch + 32;
 
+    pcx_grid_dependency_wait();
     // ---- independent of the tiles ------------------------------------------
     for (int a = tid; a < PCX_NPOINT; a += T) {
         const double v = pcx_unscale(p.pt_scal[a], x[p.pt_x[a]], p.pt_scal[PCX_NPOINT + a]);
@@ -847,6 +865,7 @@ extern "C" __global__ void __launch_bounds__(PCX_THREADS, PCX_MIN_BLOCKS)
 PCX_KERNEL_NAME(const __grid_constant__ PcxParams p)
 {
     extern __shared__ __align__(16) unsigned char pcx_smem[];
+    pcx_grid_launch_dependents();
     // large meshes: the border CTA is dispatched first and works in the shadow
     // of the tiles; small ones: last, so that it never holds a slot a tile of
     // its own instance could use
