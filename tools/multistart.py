@@ -40,7 +40,7 @@ def run(problem, batch, threads, steps=30):
 
 if __name__ == "__main__":
     for prob in ("cart_pole_swing_up", "hypersensitive"):
-        for thr in (32, 64, 128):
+        for thr in (32, 128):
             try:
                 run(prob, 4096, thr)
             except Exception as exc:
