@@ -1,0 +1,103 @@
+"""GPU edge cases: smallest meshes, one-node-per-thread limits, batched mesh
+error, C-ABI error behaviour of the sharding / mesh-error entry points."""
+import numpy as np
+import pytest
+
+from helpers import build_case, make_engine, max_err
+from pycollo_b200 import engine as E
+from pycollo_b200 import examples
+
+pytestmark = pytest.mark.gpu
+ALL = E.EVAL_C | E.EVAL_DY | E.EVAL_JAC | E.EVAL_HESS | E.EVAL_F | E.EVAL_GRAD
+
+
+def _parity(name, method, K, nodes, sizes=None, **kw):
+    low, B, scal = build_case(getattr(examples, name)(), method, K, nodes, sizes, seed=5, **kw)
+    eng = make_engine(low, scal)
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-0.5, 0.5, low.S.num_x)
+    lam = rng.standard_normal(low.S.num_c)
+    out = eng.eval_host(ALL, x, lam, 1.3)
+    ref = dict(f=[B.J(x)], grad=B.g(x), c=B.c(x), dy=B.dy(x), jac=B.G_nonzeros(x),
+               hess=B.H_nonzeros(x, 1.3, lam))
+    for k, r in ref.items():
+        got = out[k] if k == "f" else out[k][0]
+        assert max_err(got, r) <= 1e-12, (k, low.S.threads, low.S.num_tiles)
+    return low
+
+
+@pytest.mark.parametrize("method", ["lobatto", "radau"])
+@pytest.mark.parametrize("name", ["brachistochrone", "double_pendulum", "multiphase_sliding_mass"])
+def test_smallest_meshes(name, method):
+    """N = 3 is the smallest supported mesh (one interior node): as one 3-node
+    section and as two 2-node sections; N = 2 is refused with a clear error."""
+    low = _parity(name, method, 1, 3)
+    assert all(t.N == 3 for t in low.S.ph)
+    low = _parity(name, method, 2, 2)
+    assert all(t.N == 3 and t.K == 2 for t in low.S.ph)
+    with pytest.raises(ValueError, match="at least 3 mesh nodes"):
+        build_case(getattr(examples, name)(), method, 1, 2, oracle=False)
+
+
+@pytest.mark.parametrize("nodes", [3, 10, 16])
+def test_single_section_orders(nodes):
+    _parity("cart_pole_swing_up", "lobatto", 1, nodes)
+    _parity("hypersensitive", "radau", 1, nodes)
+
+
+def test_cta_sizes_follow_the_mesh():
+    """32 / 64 / 128 threads per CTA for meshes of <= 32 / <= 64 / more nodes, and a
+    tile never holds more nodes than threads."""
+    for K, want in ((10, 32), (20, 64), (30, 128)):
+        low = _parity("cart_pole_swing_up", "lobatto", K, 4)
+        assert low.S.threads == want and low.S.max_tile_nodes <= want
+    # one tile per instance takes the single-CTA path (tile + border pass in one CTA)
+    low = _parity("free_flying_robot", "lobatto", 10, 4)
+    assert low.S.num_tiles == 1
+
+
+def test_many_small_tiles_with_sections_as_large_as_a_tile():
+    # sections of 10 nodes with tiles capped at 10 nodes: one section per tile
+    _parity("space_shuttle_reentry", "lobatto", 12, 10, max_tile_nodes=10)
+    _parity("double_pendulum", "radau", 9, [10, 2, 10, 2, 10, 2, 10, 2, 10], max_tile_nodes=11)
+
+
+def test_batched_mesh_error_matches_single():
+    from pycollo_b200.mesh import Mesh, PhaseMesh
+    from pycollo_b200.mesh_refinement import MeshErrorEvaluator
+    from pycollo_b200.quadrature import Quadrature
+    ocp = examples.free_flying_robot()
+    ocp.settings.scaling_method = "none"
+    mesh = Mesh(Quadrature("lobatto"), [PhaseMesh(7, None, [4, 5, 3, 6, 4, 2, 5])], 2, 16)
+    one = MeshErrorEvaluator(ocp, mesh)
+    many = MeshErrorEvaluator(ocp, mesh, batch=3)
+    S = one.engine.S
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-0.3, 0.3, (3, S.num_x))
+    res = many(X)
+    for b in range(3):
+        single = one(X[b])
+        for (a, r, m), (ab, rb, mb) in zip(single, res):
+            assert np.array_equal(a, ab[b]) and np.array_equal(r, rb[b]) and np.array_equal(m, mb[b])
+    assert res[0][2].shape == (3, 7)
+
+
+def test_shard_and_mesh_error_argument_errors():
+    low, _, scal = build_case(examples.cart_pole_swing_up(), "lobatto", 200, 4, oracle=False)
+    eng = E.Engine(low.S, low.layouts, low.header)
+    x = np.zeros(low.S.num_x)
+    with pytest.raises(E.PcxError, match="pcx_set_scaling"):
+        eng.mesh_error_host(x)                      # scaling not set yet
+    eng.set_scaling(*scal)
+    with pytest.raises(E.PcxError, match="tile range"):
+        eng.set_shard(3, 2)
+    with pytest.raises(E.PcxError, match="tile range"):
+        eng.set_shard(0, low.S.num_tiles + 1)
+    import torch
+    xd = torch.zeros(low.S.num_x, dtype=torch.float64, device="cuda")
+    jd = torch.zeros(low.S.nnz_g, dtype=torch.float64, device="cuda")
+    with pytest.raises(E.PcxError, match="pcx_set_shard"):
+        eng.apply_border(E.EVAL_JAC, xd, jac=jd)    # not sharded
+    eng.set_shard(0, low.S.num_tiles)               # the full range is "not sharded" again
+    out = eng.eval_host(E.EVAL_JAC, x)
+    assert np.all(np.isfinite(out["jac"]))
