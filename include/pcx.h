@@ -169,6 +169,22 @@ int pcx_mesh_error(pcx_engine* e, const double* x_ph, double* abs_err,
 /* lengths (per instance) of abs_err/rel_err and of max_rel                    */
 int pcx_mesh_error_sizes(const pcx_engine* e, int64_t* n_err, int64_t* n_sections);
 
+/* ---- solution re-fit onto the p+1 mesh ---
+ * Replaces SolutionABC.interpolate_solution_{lobatto,radau}
+ * (pycollo/solution/solution_abc.py:60-142: per state and section a Legendre fit
+ * of dy*T/2 integrated from the section's first value; per control a polynomial
+ * fit) + PattersonRaoMeshRefinement.construct_x_ph / eval_polynomials
+ * (mesh_refinement.py:160-204) for an engine on the ITERATION mesh: from the
+ * solution x (user basis, engine x layout) and dy (pcx_eval_dy) it writes x_ph,
+ * the solution on the p+1 mesh in the x layout of the ph-mesh engine
+ * (section-boundary values copied, interior ph nodes from the per-section
+ * interpolants, q / t / s copied), ready for pcx_mesh_error.  The fits are applied
+ * as precomputed per-order matrices (exact interpolants; the reference's
+ * numpy least-squares fits in the [0,1] window lose ~1e-12 at order 10).      */
+int pcx_refit_to_ph(pcx_engine* e, const double* x_user, const double* dy,
+                    double* x_ph, int space, void* stream);
+int pcx_refit_size(const pcx_engine* e, int64_t* num_x_ph);
+
 /* Sizes (per instance) -- Casadi.evaluate_G_num_nonzero backend.py:1763-1771 */
 int pcx_sizes(const pcx_engine* e, int64_t* num_x, int64_t* num_c, int64_t* num_dy,
               int64_t* nnz_jac, int64_t* nnz_hess, int32_t* batch);

@@ -63,6 +63,11 @@ struct PcxParams {
     const int* border_grp; const i64* border_slot; const int* border_ptr;
     const int* border_bv; const int* border_rs; const double* border_coef;
     const i64* err_desc;    // mesh-error pass, 12 per phase: x_off,c_off,N,K,NY,sec_node_off,err_off,sec_off,mmax
+    // solution re-fit onto the p+1 mesh (pcx_refit_to_ph): 16 i64 per phase + one
+    // global row, 2 doubles per phase (fixed t0 / tF), the per-order Cy / Pu
+    // matrices and their offsets (2 ints per order)
+    const i64* refit_desc; const double* refit_const;
+    const double* refit_tab; const int* refit_off;
     const i64* pt_x;        // x index of each point variable
     const double* pt_scal;  // V then r of each point variable
 };

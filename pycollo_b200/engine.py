@@ -88,6 +88,8 @@ def load_library(rebuild=False):
     lib.pcx_set_shard.argtypes = [vp, i32, i32]
     lib.pcx_shard_buffer.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
     lib.pcx_apply_border.argtypes = [vp, i32, dp, dp, dp, dp, dp, dp, dp, dp, vp]
+    lib.pcx_refit_to_ph.argtypes = [vp, dp, dp, dp, i32, vp]
+    lib.pcx_refit_size.argtypes = [vp, ctypes.POINTER(i64)]
     lib.pcx_mesh_error.argtypes = [vp, dp, dp, dp, dp, i32, vp]
     lib.pcx_mesh_error_sizes.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     _LIB = lib
@@ -103,6 +105,8 @@ _TABLE_DTYPES = {
     "pbase": np.int64, "border_grp": np.int32, "border_slot": np.int64,
     "border_ptr": np.int32, "border_bv": np.int32, "border_rs": np.int32,
     "pt_x": np.int64, "err_desc": np.int64,
+    "refit_desc": np.int64, "refit_const": np.float64, "refit_tab": np.float64,
+    "refit_off": np.int32,
 }
 
 
@@ -165,6 +169,34 @@ def build_tables(S, layouts):
         eo += ph.K * lay.pd.NY * mmax
         so += ph.K
     t["err_desc"] = ed.ravel()
+    # solution re-fit onto the p+1 mesh (pcx_refit_to_ph): per-order Cy / Pu
+    # matrices (quadrature.refit_matrices) and the per-phase layout of x and x_ph
+    quad = S.meshes[0].quadrature
+    omax = max(S.orders)
+    tab, off = [], np.zeros(2 * (omax + 1), dtype=np.int32)
+    for n in S.orders:
+        Cy, Pu = quad.refit_matrices(n)
+        off[2 * n] = sum(len(a) for a in tab)
+        tab.append(Cy.ravel())
+        off[2 * n + 1] = sum(len(a) for a in tab)
+        tab.append(Pu.ravel())
+    t["refit_tab"] = np.concatenate(tab)
+    t["refit_off"] = off
+    rd = np.zeros((len(S.ph) + 1, 16), dtype=np.int64)
+    rc = np.zeros((len(S.ph), 2))
+    xph = work = 0
+    for ip, (ph, lay, irp) in enumerate(zip(S.ph, layouts, S.ir.phases)):
+        pd = lay.pd
+        NU = pd.NV - pd.NY
+        nqt = irp.n_q + irp.n_t
+        rd[ip, :12] = (ph.x_off, ph.N, ph.K, pd.NY, NU, nqt, ph.dy_off, ph.sec_off + ip,
+                       ph.sec_off, xph, ph.t_cols[0], ph.t_cols[1])
+        rc[ip] = ph.t_const
+        xph += pd.NV * (ph.N + ph.K) + nqt
+        work += ph.K * pd.NV
+    rd[-1, :5] = (S.s_off, S.NS, xph, xph + S.NS, work)
+    t["refit_desc"] = rd.ravel()
+    t["refit_const"] = rc.ravel()
     return {k: np.ascontiguousarray(v, dtype=_TABLE_DTYPES[k]) for k, v in t.items()}
 
 
@@ -360,6 +392,26 @@ class Engine:
             self.h, what, _ptr(x), _ptr(lam), _ptr(sigma), _ptr(f), _ptr(grad), _ptr(c),
             _ptr(jac), _ptr(hess), ctypes.c_void_p(stream) if stream else None),
             "pcx_apply_border")
+
+    # -- solution re-fit onto the p+1 mesh (row N2) --------------------------
+    def refit_size(self):
+        n = ctypes.c_int64()
+        self._check(self.lib.pcx_refit_size(self.h, ctypes.byref(n)), "pcx_refit_size")
+        return int(n.value)
+
+    def refit_to_ph_host(self, x_user, dy):
+        S, B = self.S, self.batch
+        x = np.ascontiguousarray(x_user, dtype=np.float64).reshape(B, S.num_x)
+        d = np.ascontiguousarray(dy, dtype=np.float64).reshape(B, S.num_dy)
+        out = np.empty((B, self.refit_size()))
+        self._check(self.lib.pcx_refit_to_ph(self.h, _ptr(x), _ptr(d), _ptr(out), PCX_HOST, None),
+                    "pcx_refit_to_ph")
+        return out[0] if B == 1 else out
+
+    def refit_to_ph_ptr(self, x_user, dy, x_ph, space=PCX_DEVICE, stream=None):
+        self._check(self.lib.pcx_refit_to_ph(
+            self.h, _ptr(x_user), _ptr(dy), _ptr(x_ph), space,
+            ctypes.c_void_p(stream) if stream else None), "pcx_refit_to_ph")
 
     def mesh_error_sizes(self):
         ne, ns = ctypes.c_int64(), ctypes.c_int64()

@@ -67,15 +67,32 @@ class PattersonRaoMeshRefinement:
         self.evaluator = MeshErrorEvaluator(self.ocp, self.it.mesh, device=self.it.device,
                                             collocation_points_max=s.collocation_points_max)
         self.ph_mesh = self.evaluator.ph_mesh
-        x_ph, self.y_ph, self.u_ph = self.construct_x_ph()
-        self.x_ph = x_ph
-        res = self.evaluator(x_ph)
+        self.x_ph = self.construct_x_ph_device()
+        res = self.evaluator(self.x_ph)
         self.absolute_mesh_errors = [r[0] for r in res]
         self.relative_mesh_errors = [r[1] for r in res]
         self.maximum_relative_mesh_errors = [r[2] for r in res]
 
+    def construct_x_ph_device(self):
+        """``mesh_refinement.py:160-204`` + ``solution_abc.py:60-142`` on the device
+        (``pcx_refit_to_ph``): the per-section fits are applied as per-order
+        matrices to the solution and its state derivatives."""
+        it, sol = self.it, self.sol
+        x_user = it.scaling.unscale_x(sol.x)
+        dy = np.concatenate([np.ravel(p.dy) for p in sol.phase_data]) \
+            if sol.phase_data else np.zeros(0)
+        x_ph = it.create_engine().refit_to_ph_host(x_user, dy)
+        self.y_ph, self.u_ph = [], []
+        for t, irp in zip(self.evaluator.low.S.ph, self.backend.ir.phases):
+            ny, nu = irp.n_y, irp.n_u
+            blk = x_ph[t.x_off:t.x_off + (ny + nu) * t.N].reshape(ny + nu, t.N)
+            self.y_ph.append(blk[:ny])
+            self.u_ph.append(blk[ny:])
+        return x_ph
+
     def construct_x_ph(self):
-        """``mesh_refinement.py:160-204``."""
+        """``mesh_refinement.py:160-204`` with the reference's numpy polynomial
+        objects (host mirror; the product path is ``construct_x_ph_device``)."""
         parts, y_all, u_all = [], [], []
         for ip, p_data in enumerate(self.sol.phase_data):
             bnd = self.it.mesh.mesh_index_boundaries[ip]

@@ -179,7 +179,10 @@ class Quadrature:
             raise ValueError("a mesh section needs at least two nodes")
         tab = self._cache.get(order)
         if tab is None and getattr(self, "_source", None) is not None:
-            tab = self._cache[order] = self._adopted(order)
+            try:
+                tab = self._cache[order] = self._adopted(order)
+            except KeyError:            # order absent from an adopted table set:
+                tab = None              # generate it (only auxiliary operators ask)
         if tab is None:
             tab = (self._lobatto(order) if self.method == LOBATTO
                    else self._radau(order))
@@ -233,6 +236,49 @@ class Quadrature:
     def A_matrix(self, order):
         """Integration block: (order-1) x order (``pycollo/quadrature.py:170``)."""
         return self._tables(order)["butcher"][1:, :]
+
+    def refit_matrices(self, order):
+        """Per-section re-fit operators of the solution post-processing
+        (``pycollo/solution/solution_abc.py:60-142``) in matrix form, on the local
+        coordinate ``xi`` in [-1, 1] of a section with ``order`` nodes, evaluated
+        at the ``order - 1`` interior nodes ``zeta_j`` of the same section on the
+        p+1 mesh (``order + 1`` nodes, ``mesh_refinement.py:75-86``):
+
+        * ``Cy[j, m] = int_{-1}^{zeta_j} L_m(xi) dxi`` -- the reference fits a
+          Legendre series through ``dy * T/2`` at the section's nodes and
+          integrates it from the section start (``Legendre.fit(...).integ(k=y0)``):
+          ``y_ph[j] = y[start] + stretch * (h_k / 2) * sum_m Cy[j, m] dy[m]``.
+          Lobatto interpolates all ``order`` nodes (``:86-91``); Radau the first
+          ``order - 1`` (``:117-123``), so its last column is zero.
+        * ``Pu[j, m] = L_m(zeta_j)`` over all ``order`` nodes
+          (``Polynomial.fit(t_k, u_k, deg=order-1)``, ``:94-99, 135-140``).
+        """
+        n = int(order)
+        key = ("refit", n)
+        hit = self._cache.get(key)
+        if hit is not None:
+            return hit
+        leg = np.polynomial.legendre
+        xi = np.array(self.quadrature_point(n), dtype=np.float64)
+        zeta = np.array(self.quadrature_point(n + 1), dtype=np.float64)
+        if self.method == RADAU:                 # the stored last point is a placeholder
+            xi[-1] = 1.0
+            zeta[-1] = 1.0
+        zin = zeta[1:n]
+
+        def basis(nodes):
+            V = leg.legvander(nodes, len(nodes) - 1)
+            return np.linalg.solve(V, np.eye(len(nodes)))      # column m: series of L_m
+
+        Pu = leg.legval(zin, basis(xi)).T                       # (n-1, n)
+        fit_nodes = xi if self.method == LOBATTO else xi[:-1]
+        coef = basis(fit_nodes)
+        Cy = np.zeros((n - 1, n))
+        for m in range(len(fit_nodes)):
+            integ = leg.legint(coef[:, m], lbnd=-1.0)
+            Cy[:, m] = leg.legval(zin, integ)
+        self._cache[key] = (Cy, Pu)
+        return Cy, Pu
 
     def D_matrix(self, order):
         """Difference block ``[1 | -I]`` (``pycollo/quadrature.py:165-168``)."""

@@ -147,8 +147,14 @@ def test_gpu_mesh_refinement_from_solution():
                                 ph.mesh_index_boundaries[ip], ph.tau[ip])
     u_ph = OM.interpolate_to_ph(pd.u, up, mesh.mesh_index_boundaries[ip],
                                 ph.mesh_index_boundaries[ip], ph.tau[ip])
-    assert np.allclose(y_ph, mr.y_ph[ip], atol=1e-13)
-    assert np.allclose(u_ph, mr.u_ph[ip], atol=1e-13)
+    # device re-fit (pcx_refit_to_ph) vs the reference-style numpy fits: order 5
+    scale = 1.0 + np.abs(pd.y).max()
+    assert np.max(np.abs(y_ph - mr.y_ph[ip])) <= 1e-12 * scale
+    assert np.max(np.abs(u_ph - mr.u_ph[ip])) <= 1e-12 * (1.0 + np.abs(pd.u).max())
+    # ... and vs the host mirror that uses the same numpy polynomial objects
+    x_ph_host, y_host, u_host = mr.construct_x_ph()
+    assert x_ph_host.shape == mr.x_ph.shape
+    assert np.max(np.abs(x_ph_host - mr.x_ph)) <= 1e-12 * (1.0 + np.abs(x_ph_host).max())
     low = mr.evaluator.low
     B = BlockwiseNLP(ocp, low.ir.full_bounds,
                      [dict(N=m.N, sI=m.sI_matrix, sA=m.sA_matrix, W=m.W_matrix) for m in ph.p],
@@ -158,3 +164,81 @@ def test_gpu_mesh_refinement_from_solution():
                                   pd.stretch, ph.N_K[ip], ph.mesh_index_boundaries[ip])
     assert np.max(np.abs(mr.absolute_mesh_errors[ip] - a)) <= 1e-12 * (1 + np.abs(mr.x_ph).max())
     assert np.max(np.abs(mr.maximum_relative_mesh_errors[ip] - m)) <= 1e-12
+
+
+REFIT_CASES = [("free_flying_robot", "lobatto", [4, 6, 3, 8, 5, 4, 9, 2]),
+               ("free_flying_robot", "radau", [4, 6, 3, 8, 5, 4, 9, 3]),
+               ("multiphase_sliding_mass", "lobatto", [3, 5, 4, 6, 2, 7, 4, 5]),
+               ("space_shuttle_reentry", "radau", [5, 4, 7, 3, 6, 4, 3, 8])]
+
+
+def test_refit_matrices_are_exact_on_polynomials():
+    """quadrature.refit_matrices: integral of the interpolant / interpolant at the
+    interior ph nodes, exact (1e-14) for polynomial data of the section's degree,
+    where the reference's numpy fits in the [0,1] window lose digits with the order."""
+    for method in ("lobatto", "radau"):
+        q = Quadrature(method)
+        for n in (2, 3, 4, 7, 10, 16):
+            Cy, Pu = q.refit_matrices(n)
+            xi = np.array(q.quadrature_point(n), dtype=float)
+            zeta = np.array(q.quadrature_point(n + 1), dtype=float)
+            if method == "radau":
+                xi[-1] = zeta[-1] = 1.0
+            zin = zeta[1:n]
+            deg_y = n - 1 if method == "lobatto" else n - 2
+            for d in range(deg_y + 1):
+                exact = (zin ** (d + 1) - (-1.0) ** (d + 1)) / (d + 1)
+                assert np.max(np.abs(Cy @ xi ** d - exact)) <= 2e-14, (method, n, d)
+            for d in range(n):
+                assert np.max(np.abs(Pu @ xi ** d - zin ** d)) <= 2e-14, (method, n, d)
+            if method == "radau":
+                assert np.all(Cy[:, -1] == 0.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("problem,method,nodes", REFIT_CASES)
+def test_gpu_refit_to_ph_matches_reference_fits(problem, method, nodes):
+    """pcx_refit_to_ph vs the oracle's restatement of the reference's numpy fits
+    (solution_abc.py:60-142, mesh_refinement.py:160-204).  Tolerance: the numpy
+    fits themselves are only good to ~1e-12 at order 9-10 (test above)."""
+    from pycollo_b200 import engine as E
+    from pycollo_b200.backend import lower_problem
+    from pycollo_b200.mesh_refinement import create_ph_mesh
+    ocp = _problem(problem, method)
+    sizes = [0.1, 0.15, 0.05, 0.2, 0.1, 0.12, 0.08, 0.2]
+    mesh = Mesh(Quadrature(method), [PhaseMesh(len(nodes), sizes, nodes) for _ in ocp.phases], 2, 16)
+    low = lower_problem(ocp, mesh.p)
+    S = low.S
+    eng = E.Engine(S, low.layouts, low.header)
+    eng.set_scaling(np.ones(S.n_var_ocp), np.zeros(S.n_var_ocp), np.ones(S.n_con_ocp), 1.0)
+    rng = np.random.default_rng(8)
+    x = rng.uniform(0.2, 0.6, S.num_x)
+    dy = eng.eval_host(E.EVAL_DY, x)["dy"][0]
+    x_ph = eng.refit_to_ph_host(x, dy)
+    ph = create_ph_mesh(mesh, 2, 16)
+    off = 0
+    for ip, (irp, t) in enumerate(zip(low.ir.phases, S.ph)):
+        N, Nph = t.N, ph.N[ip]
+        ny, nu = irp.n_y, irp.n_u
+        y = x[t.x_off:t.x_off + ny * N].reshape(ny, N)
+        u = x[t.x_off + ny * N:t.x_off + (ny + nu) * N].reshape(nu, N)
+        d = dy[t.dy_off:t.dy_off + ny * N].reshape(ny, N)
+        tv = x[t.q_col + irp.n_q:t.q_col + irp.n_q + irp.n_t]
+        t0 = tv[0] if irp.t_needed[0] else float(irp.t0)
+        tF = tv[-1] if irp.t_needed[1] else float(irp.tF)
+        bnd, bph = mesh.mesh_index_boundaries[ip], ph.mesh_index_boundaries[ip]
+        yp, up = OM.fit_section_polys(mesh.tau[ip], y, d, u, tF - t0, bnd, mesh.N_K[ip], method)
+        y_ref = OM.interpolate_to_ph(y, yp, bnd, bph, ph.tau[ip])
+        u_ref = OM.interpolate_to_ph(u, up, bnd, bph, ph.tau[ip])
+        got_y = x_ph[off:off + ny * Nph].reshape(ny, Nph)
+        got_u = x_ph[off + ny * Nph:off + (ny + nu) * Nph].reshape(nu, Nph)
+        tol = 5e-12 * (1.0 + max(np.abs(y_ref).max(), np.abs(d).max() * abs(tF - t0)))
+        assert np.max(np.abs(got_y - y_ref)) <= tol
+        assert np.max(np.abs(got_u - u_ref)) <= 5e-12 * (1.0 + np.abs(u_ref).max())
+        assert np.array_equal(got_y[:, bph], y[:, bnd])        # boundary values are copied
+        nqt = irp.n_q + irp.n_t
+        assert np.array_equal(x_ph[off + (ny + nu) * Nph:off + (ny + nu) * Nph + nqt],
+                              x[t.q_col:t.q_col + nqt])
+        off += (ny + nu) * Nph + nqt
+    assert np.array_equal(x_ph[off:], x[S.s_off:])
+    assert off + S.NS == eng.refit_size()
