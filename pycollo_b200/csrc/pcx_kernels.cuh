@@ -366,31 +366,13 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     int* sNodeSec = sSecOrder + (nsec + 1);                    // nn
     __shared__ double sCst[1 + 2 * (NY > 0 ? NY : 1)];
 
-    // everything below depends only on the tile descriptor: all global loads of
-    // the prologue (this thread's node variables, quadrature table, section
-    // table, multipliers) are in flight together before the first barrier
-    // programmatic dependent launch: everything above touched only the engine's
-    // immutable tables; the iterate, the multipliers and every output may belong
-    // to the previous kernel in the stream, which has to be complete from here on
-    pcx_grid_dependency_wait();
-    double xt0[NV > 0 ? NV : 1];
-#pragma unroll
-    for (int a = 0; a < NV; ++a)
-        xt0[a] = (tid < nn) ? x[xo + (i64)a * N + node0 + tid] : 0.0;
-    const double xt_t0 = Ph::HAS_T0 ? x[pb[Ph::PB_T0X]] : 0.0;
-    const double xt_tF = Ph::HAS_TF ? x[pb[Ph::PB_TFX]] : 0.0;
+    // ---- table-only part of the prologue (before the dependency wait) --------
+    // quadrature table, G constants and the section table slice of the tile go to
+    // shared memory, the node -> section map is built: none of it depends on the
+    // iterate, so under programmatic dependent launch all of it overlaps the
+    // previous kernel's drain
     for (int i = tid; i < p.btab_len; i += T) sB[i] = pcx_ld_keep(p.btab + i, keep);
     if (WANT_G && tid < 1 + 2 * NY) sCst[tid] = ps[Ph::OFF_GCST + tid];
-    if (WANT_H) {
-        // multipliers of the defect rows of sections k0-1 .. k1-1
-        const int nrows = nn - 1 + prev_rows;
-        const double* lp = lam + co + (node0 - prev_rows) + tid;
-#pragma unroll 1
-        for (int r = tid; r < nrows; r += T, lp += T) {
-#pragma unroll
-            for (int i = 0; i < NY; ++i) sLam[i * lam_stride + r] = lp[(i64)i * (N - 1)];
-        }
-    }
     for (int s = tid; s <= nsec; s += T) {
         const int k = k0 - 1 + s;                  // s = 0 is the previous section
         const bool ok = (k >= 0);
@@ -400,11 +382,32 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     }
     if (tid == 0) sSecNode[nsec + 1] = nn - 1;
     __syncthreads();
-    PCX_STAMP(8);
     for (int s = tid; s < nsec; s += T) {
         const int b = sSecNode[s + 1], n = sSecOrder[s + 1];
         for (int m = 0; m < n - 1; ++m) sNodeSec[b + m] = s;
         if (s == nsec - 1) sNodeSec[b + n - 1] = s;
+    }
+    // ---- the iterate and the multipliers ------------------------------------------
+    // everything above touched only the engine's immutable tables; x, lam and
+    // every output may belong to the previous kernel in the stream, which has to
+    // be complete from here on
+    pcx_grid_dependency_wait();
+    PCX_STAMP(8);
+    double xt0[NV > 0 ? NV : 1];
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+        xt0[a] = (tid < nn) ? x[xo + (i64)a * N + node0 + tid] : 0.0;
+    const double xt_t0 = Ph::HAS_T0 ? x[pb[Ph::PB_T0X]] : 0.0;
+    const double xt_tF = Ph::HAS_TF ? x[pb[Ph::PB_TFX]] : 0.0;
+    if (WANT_H) {
+        // multipliers of the defect rows of sections k0-1 .. k1-1
+        const int nrows = nn - 1 + prev_rows;
+        const double* lp = lam + co + (node0 - prev_rows) + tid;
+#pragma unroll 1
+        for (int r = tid; r < nrows; r += T, lp += T) {
+#pragma unroll
+            for (int i = 0; i < NY; ++i) sLam[i * lam_stride + r] = lp[(i64)i * (N - 1)];
+        }
     }
     __syncthreads();
     PCX_STAMP(1);
@@ -540,6 +543,13 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
             for (int a = 0; a < NV; ++a) out_grad[xo + (i64)a * N + m] = 0.0;
         }
     }
+#ifdef PCX_DEBUG_TIMELINE
+    if ((tid & 31) == 0 && (tid >> 5) < 4) {           // per-warp end of the node phase
+        unsigned long long tw;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw));
+        p.partials[(i64)tile * 16 + 11 + (tid >> 5)] = (double)(tw & ((1ull << 40) - 1));
+    }
+#endif
     if (WANT_GRAD && tile == 0) {
         // non-node entries (q, t of every phase, s) are zeroed once; the border
         // pass overwrites the structural ones afterwards

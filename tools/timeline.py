@@ -75,3 +75,11 @@ slow = np.argsort(-node_d)[:12]
 print("slowest node phases:", [(int(i), int(smid[i]), round(float(node_d[i]), 2)) for i in slow])
 per_sm_end = np.array([rel[smid == s_, 5].max() for s_ in np.flatnonzero(cnt)])
 print("per-SM last CTA end: min %.2f med %.2f max %.2f us" % (per_sm_end.min(), np.median(per_sm_end), per_sm_end.max()))
+
+# warps of one CTA: how far apart do they leave the node phase (the CTA-wide barrier
+# before the scatter makes the early ones wait for the last)
+w = (raw_stamps[:, 11:15] - t0) / 1e3
+spread = w.max(axis=1) - w.min(axis=1)
+print("intra-CTA warp skew at the end of the node phase: med %.2f p90 %.2f max %.2f us; "
+      "mean wait of a warp at the barrier %.2f us" % (np.median(spread), np.percentile(spread, 90),
+                                                     spread.max(), float((w.max(axis=1, keepdims=True) - w).mean())))
