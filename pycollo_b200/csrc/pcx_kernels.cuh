@@ -148,6 +148,91 @@ __host__ __device__ constexpr bool pcx_need_red() {
 }
 
 // ---------------------------------------------------------------------------
+// Scatter of the Jacobian values: run setup, recipe decoding, store loop.
+// A section of a given type owns, for every variable a, a fixed "period" of P_a
+// value slots; the host lists the tile as runs of consecutive same-type sections
+// (one run per tile on a uniform mesh, plus a one-section run in the first and
+// last tile).  Thread t takes ONE slot u of the concatenated period (all
+// variables): its 64-bit recipe word is decoded once per run and the loop over
+// the run's sections is LDS, DFMA, STG + two pointer bumps.  Consecutive threads
+// write consecutive addresses inside a variable's period, and a variable's
+// periods of consecutive sections are back to back.
+// ---------------------------------------------------------------------------
+struct PcxRun { int s_lo, s_hi, rec0, Ptot, per, u0, sc0, nstep; const int* tv; };
+struct PcxSlot { double bcoef, cc; i64 o; int dp, dstep, ostep, cnt; };
+
+template <class Ph>
+__device__ __forceinline__ bool pcx_run_setup(const PcxParams& p, const int run, const int tid,
+                                              const unsigned long long keep,
+                                              const int* sSecOrder, PcxRun& R) {
+    constexpr int T = PCX_THREADS;
+    R.s_lo = pcx_ld_keep(p.run_slo + run, keep);
+    R.s_hi = pcx_ld_keep(p.run_shi + run, keep);
+    R.tv = p.type_var_off + pcx_ld_keep(p.run_type + run, keep) * (p.nvmax + 1);
+    R.rec0 = R.tv[0];
+    R.Ptot = R.tv[Ph::NV] - R.rec0;                  // slots per section, all variables
+    if (R.Ptot == 0) return false;
+    R.per = 1; R.u0 = tid; R.sc0 = R.s_lo;
+    if (R.Ptot < T) {                                // several sections per pass
+        R.per = T / R.Ptot;
+        const int q = tid / R.Ptot;
+        R.u0 = tid - q * R.Ptot;
+        R.sc0 = R.s_lo + q;
+        if (q >= R.per) return false;
+    }
+    // all sections of a run share one type, hence one order n_k: the first node
+    // of section sc is nd0 + (sc - s_lo) * (n_k - 1), so the staged-derivative
+    // pointer advances by a constant (1 for the previous-section copies)
+    R.nstep = sSecOrder[R.s_lo + 1] - 1;
+    return true;
+}
+
+// dp is an offset (in doubles) from the base of the dynamic shared memory (sB);
+// constant-only slots read the 0.0 sentinel sB[0] with stride 0
+template <class Ph>
+__device__ __forceinline__ bool pcx_decode_slot(const PcxParams& p, const int run, const int u,
+                                                const PcxRun& R, const unsigned long long keep,
+                                                const double* sB, const double* cst,
+                                                const int* sSecNode, const int sD_off,
+                                                const int sDP_off, const int nnp, const int nsp,
+                                                PcxSlot& S) {
+    const unsigned long long w = pcx_ld_keep(p.recipes + R.rec0 + u, keep);
+    const u32 lo = (u32)w;
+    if (lo >> RC_SKIP_BIT) return false;
+    const int a = (int)((w >> 32) & 0xffu);
+    const int local = (int)(w >> 40);
+    const int Pa = R.tv[a + 1] - R.tv[a];
+    const int e = lo & ((1u << RC_E_BITS) - 1);
+    const int bi = (lo >> RC_B_SHIFT) & ((1u << RC_B_BITS) - 1);
+    const int mloc = (lo >> RC_M_SHIFT) & ((1u << RC_M_BITS) - 1);
+    S.cc = cst[(lo >> RC_C_SHIFT) & ((1u << RC_C_BITS) - 1)];
+    const bool prev = (lo >> RC_PREV_BIT) & 1u;
+    S.bcoef = sB[bi];                                // 1.0 for plain slots
+    S.dp = 0; S.dstep = 0;
+    if (e) {
+        S.dp = prev ? sDP_off + (e - 1) * nsp + R.sc0
+                    : sD_off + (e - 1) * nnp + mloc + sSecNode[R.sc0 + 1];
+        S.dstep = prev ? R.per : R.per * R.nstep;
+    }
+    S.o = pcx_ld_keep(p.run_gbase + (i64)run * p.nvmax + a, keep) + local
+          + (i64)(R.sc0 - R.s_lo) * Pa;
+    S.ostep = R.per * Pa;
+    S.cnt = (R.s_hi - R.sc0 + R.per - 1) / R.per;
+    return true;
+}
+
+// no divergent branch: every slot kind is  value = bcoef * staged + constant
+__device__ __forceinline__ void pcx_store_run(double* o, const int ostep, const double* dp,
+                                              const int dstep, const double bcoef,
+                                              const double cc, const int cnt) {
+#pragma unroll 4
+    for (int it = 0; it < cnt; ++it) {
+        *o = bcoef * (*dp) + cc;
+        o += ostep; dp += dstep;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Destination of the per-node results of the generated body PcxPhase<P>::eval.
 // Every method is a compile-time-indexed store: nothing the body computes stays
 // live after it has been produced (a problem like the Delta III launcher has
@@ -364,6 +449,10 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     int* sSecNode = reinterpret_cast<int*>(sRed + T / 32);     // nsec+2 (prev first)
     int* sSecOrder = sSecNode + (nsec + 2);                    // nsec+1 (prev first)
     int* sNodeSec = sSecOrder + (nsec + 1);                    // nn
+    // the thread's first scatter work item, decoded in the prologue
+    __shared__ double sPreCoef[2 * T];
+    __shared__ i64 sPreO[T];
+    __shared__ int sPreDp[T], sPreDstep[T], sPreOstep[T], sPreCnt[T];
     __shared__ double sCst[1 + 2 * (NY > 0 ? NY : 1)];
 
     // ---- table-only part of the prologue (before the dependency wait) --------
@@ -386,6 +475,28 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         const int b = sSecNode[s + 1], n = sSecOrder[s + 1];
         for (int m = 0; m < n - 1; ++m) sNodeSec[b + m] = s;
         if (s == nsec - 1) sNodeSec[b + n - 1] = s;
+    }
+    // the scatter's tables (run descriptor -> type -> recipe word -> slot base) are
+    // a chain of dependent loads: walked here, in the shadow of the previous
+    // kernel, instead of between the node phase and the first store
+    bool pre_more = false;
+    if (WANT_G) {
+        sPreCnt[tid] = 0;
+        if (nruns > 0) {
+            PcxRun run;
+            if (pcx_run_setup<Ph>(p, run0, tid, keep, sSecOrder, run)) {
+                PcxSlot sl;
+                if (pcx_decode_slot<Ph>(p, run0, run.u0, run, keep, sB, sCst, sSecNode,
+                                        (int)(sD - sB), (int)(sDP - sB), nnp, nsp, sl)) {
+                    sPreCoef[2 * tid] = sl.bcoef; sPreCoef[2 * tid + 1] = sl.cc;
+                    sPreO[tid] = sl.o; sPreDp[tid] = sl.dp; sPreDstep[tid] = sl.dstep;
+                    sPreOstep[tid] = sl.ostep; sPreCnt[tid] = sl.cnt;
+                }
+            }
+            // CTA-uniform: is there anything beyond one work item per thread?
+            const int* tv0 = p.type_var_off + pcx_ld_keep(p.run_type + run0, keep) * (p.nvmax + 1);
+            pre_more = (nruns > 1) || (tv0[NV] - tv0[0] > T);
+        }
     }
     // ---- the iterate and the multipliers ------------------------------------------
     // everything above touched only the engine's immutable tables; x, lam and
@@ -624,72 +735,24 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         }
     }
 
-    // ---- coalesced scatter of the Jacobian values ------------------------------
-    // A section of a given type owns, for every variable a, a fixed "period" of
-    // P_a value slots; the host lists the tile as runs of consecutive same-type
-    // sections (one run per tile on a uniform mesh, plus a one-section run in the
-    // first and last tile).  Thread t takes ONE slot u of the concatenated period
-    // (all variables): its 64-bit recipe word is decoded once per run and the
-    // loop over the run's sections is  2 x LDS, DMUL, DFMA, STG + pointer bumps.
-    // Consecutive threads write consecutive addresses inside a variable's period,
-    // and a variable's periods of consecutive sections are back to back.
+    // ---- coalesced scatter of the Jacobian values (see pcx_store_run) ----------
     if (WANT_G) {
-        const double* cst = sCst;
-        const int nvp1 = p.nvmax + 1;
+        // the thread's first work item was decoded in the prologue
+        if (sPreCnt[tid] > 0)
+            pcx_store_run(out_g + sPreO[tid], sPreOstep[tid], sB + sPreDp[tid], sPreDstep[tid],
+                          sPreCoef[2 * tid], sPreCoef[2 * tid + 1], sPreCnt[tid]);
+        if (pre_more) {
 #pragma unroll 1
-        for (int r = 0; r < nruns; ++r) {
-            const int s_lo = pcx_ld_keep(p.run_slo + run0 + r, keep);
-            const int s_hi = pcx_ld_keep(p.run_shi + run0 + r, keep);
-            const int* tv = p.type_var_off + pcx_ld_keep(p.run_type + run0 + r, keep) * nvp1;
-            const int rec0 = tv[0];
-            const int Ptot = tv[NV] - rec0;                  // slots per section, all variables
-            if (Ptot == 0) continue;
-            int per = 1, u0 = tid, sc0 = s_lo;
-            if (Ptot < T) {                                  // several sections per pass
-                per = T / Ptot;
-                const int q = tid / Ptot;
-                u0 = tid - q * Ptot;
-                sc0 = s_lo + q;
-                if (q >= per) continue;
-            }
-            // all sections of a run share one type, hence one order n_k: the
-            // first node of section sc is nd0 + (sc - s_lo) * (n_k - 1), so the
-            // staged-derivative pointer advances by a constant (1 for the
-            // previous-section copies); constant-only slots read the 0.0
-            // sentinel sB[0] with stride 0.  No divergent branch in the loop:
-            // LDS, DFMA, STG + two pointer bumps.
-            const int nstep = sSecOrder[s_lo + 1] - 1;
-            for (int u = u0; u < Ptot; u += T) {
-                const unsigned long long w = pcx_ld_keep(p.recipes + rec0 + u, keep);
-                const u32 lo = (u32)w;
-                if (!(lo >> RC_SKIP_BIT)) {
-                    const int a = (int)((w >> 32) & 0xffu);
-                    const int local = (int)(w >> 40);
-                    const int Pa = tv[a + 1] - tv[a];
-                    const int e = lo & ((1u << RC_E_BITS) - 1);
-                    const int bi = (lo >> RC_B_SHIFT) & ((1u << RC_B_BITS) - 1);
-                    const int mloc = (lo >> RC_M_SHIFT) & ((1u << RC_M_BITS) - 1);
-                    const double cc = cst[(lo >> RC_C_SHIFT) & ((1u << RC_C_BITS) - 1)];
-                    const bool prev = (lo >> RC_PREV_BIT) & 1u;
-                    const double bcoef = sB[bi];                     // 1.0 for plain slots
-                    const double* dp = sB;
-                    int dstep = 0;
-                    if (e) {
-                        dp = prev ? sDP + (e - 1) * nsp + sc0
-                                  : sD + (e - 1) * nnp + mloc + sSecNode[sc0 + 1];
-                        dstep = prev ? per : per * nstep;
-                    }
-                    double* o = out_g + pcx_ld_keep(p.run_gbase + (i64)(run0 + r) * p.nvmax + a, keep) + local
-                                + (i64)(sc0 - s_lo) * Pa;
-                    const int ostep = per * Pa;
-                    const int cnt = (s_hi - sc0 + per - 1) / per;
-#pragma unroll 4
-                    for (int it = 0; it < cnt; ++it) {
-                        *o = bcoef * (*dp) + cc;
-                        o += ostep; dp += dstep;
-                    }
+            for (int r = 0; r < nruns; ++r) {
+                PcxRun run;
+                if (!pcx_run_setup<Ph>(p, run0 + r, tid, keep, sSecOrder, run)) continue;
+                for (int u = run.u0 + (r == 0 ? T : 0); u < run.Ptot; u += T) {
+                    PcxSlot sl;
+                    if (pcx_decode_slot<Ph>(p, run0 + r, u, run, keep, sB, sCst, sSecNode,
+                                            (int)(sD - sB), (int)(sDP - sB), nnp, nsp, sl))
+                        pcx_store_run(out_g + sl.o, sl.ostep, sB + sl.dp, sl.dstep, sl.bcoef, sl.cc, sl.cnt);
+                    if (run.Ptot < T) break;
                 }
-                if (Ptot < T) break;
             }
         }
     }
