@@ -78,7 +78,8 @@ if os.path.exists(src):
     with open(os.path.join(P, f"r{rnd}_launches_summary.csv"), "w") as fh:
         fh.write("# ncu launch list of `python bench.py --steps 30 --warmup 5 --no-cpu-baseline`\n"
                  "# (--metrics gpu__time_duration.sum --clock-control none): per-launch times are cold-cache and\n"
-                 "# serialised by ncu -- compare SHARES of the step, not absolutes\n"
+                 "# serialised by ncu -- compare SHARES of the step, not absolutes.  torch kernels in the list are the\n"
+                 "# synthetic-input generation of bench.py's informational `amortised` section (outside every timed region)\n"
                  "kernel,launches,total_ns,median_ns,min_ns,max_ns,share_of_gpu_time\n")
         for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
             v = sorted(v)
