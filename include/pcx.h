@@ -185,6 +185,20 @@ int pcx_refit_to_ph(pcx_engine* e, const double* x_user, const double* dy,
                     double* x_ph, int space, void* stream);
 int pcx_refit_size(const pcx_engine* e, int64_t* num_x_ph);
 
+/* ---- guess interpolation to a new mesh -----
+ * Replaces Iteration.interpolate_guess_to_mesh (pycollo/iteration.py:86-194:
+ * scipy interp1d, linear, fill_value="extrapolate", per state / control row) for
+ * an engine on the NEW mesh: x_prev is a solution or guess (user basis) in the x
+ * layout of a previous mesh with prev_N[p] nodes in phase p at abscissae
+ * prev_tau (phases concatenated), tau the new mesh's abscissae (phases
+ * concatenated, N_p each).  y and u rows are interpolated with interp1d's own
+ * formula slope*(t - t_lo) + y_lo, lo/hi from a left bisection clipped to
+ * [1, M-1]; q, t and s are copied (iteration.py:166-168).  prev_N is a host
+ * array of num_phases entries whatever `space` is.                            */
+int pcx_interp_guess(pcx_engine* e, const double* x_prev, const double* prev_tau,
+                     const int64_t* prev_N, const double* tau, double* x_guess,
+                     int space, void* stream);
+
 /* Sizes (per instance) -- Casadi.evaluate_G_num_nonzero backend.py:1763-1771 */
 int pcx_sizes(const pcx_engine* e, int64_t* num_x, int64_t* num_c, int64_t* num_dy,
               int64_t* nnz_jac, int64_t* nnz_hess, int32_t* batch);

@@ -88,6 +88,7 @@ def load_library(rebuild=False):
     lib.pcx_set_shard.argtypes = [vp, i32, i32]
     lib.pcx_shard_buffer.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
     lib.pcx_apply_border.argtypes = [vp, i32, dp, dp, dp, dp, dp, dp, dp, dp, vp]
+    lib.pcx_interp_guess.argtypes = [vp, dp, dp, dp, dp, dp, i32, vp]
     lib.pcx_refit_to_ph.argtypes = [vp, dp, dp, dp, i32, vp]
     lib.pcx_refit_size.argtypes = [vp, ctypes.POINTER(i64)]
     lib.pcx_mesh_error.argtypes = [vp, dp, dp, dp, dp, i32, vp]
@@ -392,6 +393,20 @@ class Engine:
             self.h, what, _ptr(x), _ptr(lam), _ptr(sigma), _ptr(f), _ptr(grad), _ptr(c),
             _ptr(jac), _ptr(hess), ctypes.c_void_p(stream) if stream else None),
             "pcx_apply_border")
+
+    # -- guess interpolation to this engine's mesh (row N3) ----------------------
+    def interp_guess_host(self, x_prev, prev_tau, tau):
+        """``pcx_interp_guess``: ``x_prev`` in the x layout of a previous mesh whose
+        per-phase abscissae are the arrays ``prev_tau``; ``tau`` = this mesh's."""
+        S = self.S
+        xp = np.ascontiguousarray(x_prev, dtype=np.float64)
+        pn = np.ascontiguousarray([len(t) for t in prev_tau], dtype=np.int64)
+        pt = np.ascontiguousarray(np.concatenate(prev_tau), dtype=np.float64)
+        tt = np.ascontiguousarray(np.concatenate(tau), dtype=np.float64)
+        out = np.empty(S.num_x)
+        self._check(self.lib.pcx_interp_guess(self.h, _ptr(xp), _ptr(pt), _ptr(pn), _ptr(tt),
+                                              _ptr(out), PCX_HOST, None), "pcx_interp_guess")
+        return out
 
     # -- solution re-fit onto the p+1 mesh (row N2) --------------------------
     def refit_size(self):

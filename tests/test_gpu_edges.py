@@ -101,3 +101,35 @@ def test_shard_and_mesh_error_argument_errors():
     eng.set_shard(0, low.S.num_tiles)               # the full range is "not sharded" again
     out = eng.eval_host(E.EVAL_JAC, x)
     assert np.all(np.isfinite(out["jac"]))
+
+
+@pytest.mark.parametrize("problem", ["double_pendulum", "multiphase_sliding_mass", "free_flying_robot"])
+def test_guess_interpolation_matches_scipy_interp1d(problem):
+    """Row N3: pcx_interp_guess vs the reference's own scipy call (oracle/guess.py),
+    including abscissae a hair outside the previous mesh (extrapolation branch)."""
+    from oracle.guess import interpolate_guess_to_mesh
+    from pycollo_b200.mesh import Mesh, PhaseMesh
+    from pycollo_b200.quadrature import Quadrature
+    ocp = getattr(examples, problem)()
+    low, _, scal = build_case(ocp, "lobatto", 9, [4, 6, 3, 8, 5, 4, 9, 2, 5],
+                              [0.1, 0.15, 0.05, 0.2, 0.1, 0.12, 0.08, 0.1, 0.1], oracle=False)
+    S = low.S
+    eng = make_engine(low, scal)
+    rng = np.random.default_rng(12)
+    prev_tau, tau, ys, us, qs, ts, xprev = [], [], [], [], [], [], []
+    for irp, t, m in zip(low.ir.phases, S.ph, low.meshes):
+        M = int(rng.integers(5, 40))
+        pt = np.sort(rng.uniform(-1, 1, M))
+        pt[0], pt[-1] = -1.0, 1.0 - 1e-13          # last new node lies just outside
+        prev_tau.append(pt)
+        tau.append(np.asarray(m.tau))
+        y, u = rng.standard_normal((irp.n_y, M)), rng.standard_normal((irp.n_u, M))
+        q, tt = rng.standard_normal(irp.n_q), rng.standard_normal(irp.n_t)
+        ys.append(y); us.append(u); qs.append(q); ts.append(tt)
+        xprev += [y.ravel(), u.ravel(), q, tt]
+    s = rng.standard_normal(S.NS)
+    xprev.append(s)
+    got = eng.interp_guess_host(np.concatenate(xprev), prev_tau, tau)
+    ref = interpolate_guess_to_mesh(prev_tau, tau, ys, us, qs, ts, s)
+    assert got.shape == ref.shape == (S.num_x,)
+    assert np.max(np.abs(got - ref)) <= 1e-13 * (1.0 + np.abs(ref).max())
