@@ -234,6 +234,18 @@ class IterationScaling:
         it.push_scaling()
 
 
+def _interp1d_linear(x, y, x_new):
+    """``scipy.interpolate.interp1d(x, y, bounds_error=False,
+    fill_value="extrapolate")(x_new)`` as the reference calls it
+    (``pycollo/iteration.py:128-134``): left bisection clipped to [1, M-1], then
+    ``slope * (x_new - x_lo) + y_lo``.  Same rule as ``pcx_interp_guess``."""
+    x, y, x_new = (np.asarray(a, dtype=np.float64) for a in (x, y, x_new))
+    hi = np.clip(np.searchsorted(x, x_new), 1, len(x) - 1)
+    lo = hi - 1
+    slope = (y[hi] - y[lo]) / (x[hi] - x[lo])
+    return slope * (x_new - x[lo]) + y[lo]
+
+
 class Iteration:
     """One mesh iteration = one NLP (``pycollo/iteration.py:18-653``)."""
 
@@ -267,9 +279,9 @@ class Iteration:
         parts = []
         self.guess_y, self.guess_u = [], []
         for ip, (tau, ptau) in enumerate(zip(self.mesh.tau, prev.tau)):
-            y = np.vstack([np.interp(tau, ptau, row) for row in prev.y[ip]]) \
+            y = np.vstack([_interp1d_linear(ptau, row, tau) for row in prev.y[ip]]) \
                 if len(prev.y[ip]) else np.empty((0, len(tau)))
-            u = np.vstack([np.interp(tau, ptau, row) for row in prev.u[ip]]) \
+            u = np.vstack([_interp1d_linear(ptau, row, tau) for row in prev.u[ip]]) \
                 if len(prev.u[ip]) else np.empty((0, len(tau)))
             self.guess_y.append(y)
             self.guess_u.append(u)

@@ -311,7 +311,10 @@ struct PcxNodeSink {
         else irr[Ph::NH2VV + K] = val;
     }
     template <int K> __device__ __forceinline__ void HTV(const double val) const {
-        if (!WANT_H || !owned) return;
+        // rows of H against t0 / tF exist only for free times; with both times
+        // fixed nothing consumes these results and the compiler drops their
+        // computation (and the t-multipliers feeding it) from the body
+        if (!WANT_H || !HAS_T || !owned) return;
         if (regular) {
             if (Ph::HAS_T0) out_h[pb[Ph::PB_HT0 + K] + (m - 1)] = ps[Ph::OFF_HT0 + K] * val;
             if (Ph::HAS_TF) out_h[pb[Ph::PB_HTF + K] + (m - 1)] = ps[Ph::OFF_HTF + K] * val;
