@@ -452,6 +452,8 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     int* sSecNode = reinterpret_cast<int*>(sRed + T / 32);     // nsec+2 (prev first)
     int* sSecOrder = sSecNode + (nsec + 2);                    // nsec+1 (prev first)
     int* sNodeSec = sSecOrder + (nsec + 1);                    // nn
+    int* sAoff = sNodeSec + nn;                                // nsec+1 (prev first): A(N_k) in sB
+    int* sWoff = sAoff + (nsec + 1);                           // nsec+1 (prev first): w(N_k) in sB
     // the thread's first scatter work item, decoded in the prologue
     __shared__ double sPreCoef[2 * T];
     __shared__ i64 sPreO[T];
@@ -469,8 +471,13 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         const int k = k0 - 1 + s;                  // s = 0 is the previous section
         const bool ok = (k >= 0);
         sHk[s] = ok ? pcx_ld_keep(p.sec_h + sec_off + k, keep) : 0.0;
-        sSecOrder[s] = ok ? pcx_ld_keep(p.sec_order + sec_off + k, keep) : 0;
+        const int ord = ok ? pcx_ld_keep(p.sec_order + sec_off + k, keep) : 0;
+        sSecOrder[s] = ord;
         sSecNode[s] = ok ? (int)(pcx_ld_keep(sec_node + k, keep) - node0) : 0;
+        // where the section's quadrature tables start in sB: looked up here so the
+        // node phase reads shared memory only
+        sAoff[s] = p.order_a_off[ord];
+        sWoff[s] = p.order_w_off[ord];
     }
     if (tid == 0) sSecNode[nsec + 1] = nn - 1;
     __syncthreads();
@@ -513,6 +520,14 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         xt0[a] = (tid < nn) ? x[xo + (i64)a * N + node0 + tid] : 0.0;
     const double xt_t0 = Ph::HAS_T0 ? x[pb[Ph::PB_T0X]] : 0.0;
     const double xt_tF = Ph::HAS_TF ? x[pb[Ph::PB_TFX]] : 0.0;
+    double lam_p[NP > 0 ? NP : 1], lam_q[NQ > 0 ? NQ : 1];     // path (this node) / integral rows
+    if (WANT_H) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+            lam_p[j] = (tid < nn) ? lam[co + (i64)NY * (N - 1) + (i64)j * N + node0 + tid] : 0.0;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) lam_q[i] = lam[co + (i64)NY * (N - 1) + (i64)NP * N + i];
+    }
     if (WANT_H) {
         // multipliers of the defect rows of sections k0-1 .. k1-1
         const int nrows = nn - 1 + prev_rows;
@@ -570,8 +585,8 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         double wq = 0.0;
         if (NQ > 0 && (WANT_C || WANT_G || WANT_H)) {
             if (start_with_prev)
-                wq = __dmul_rn(sB[p.order_w_off[n_pr] + n_pr - 1], h_pr);
-            wq = __dadd_rn(wq, __dmul_rn(sB[p.order_w_off[n_k] + mloc], h_k));
+                wq = __dmul_rn(sB[sWoff[s] + n_pr - 1], h_pr);
+            wq = __dadd_rn(wq, __dmul_rn(sB[sWoff[s + 1] + mloc], h_k));
         }
 
         double muh[NF > 0 ? NF : 1], mut[NF > 0 ? NF : 1];
@@ -582,7 +597,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
 #pragma unroll
             for (int i = 0; i < NY; ++i) lacc[i] = 0.0;
             if (start_with_prev) {
-                const double* Apr = sB + p.order_a_off[n_pr] + n_pr - 1;
+                const double* Apr = sB + sAoff[s] + n_pr - 1;
                 const double* lrow = sLam + prev_rows + sSecNode[s];
                 for (int l = 0; l < n_pr - 1; ++l) {
                     const double cl = __dmul_rn(Apr[l * n_pr], h_pr);
@@ -591,7 +606,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
                 }
             }
             if (owned) {
-                const double* Ak = sB + p.order_a_off[n_k] + mloc;
+                const double* Ak = sB + sAoff[s + 1] + mloc;
                 const double* lrow = sLam + prev_rows + sSecNode[s + 1];
                 for (int l = 0; l < n_k - 1; ++l) {
                     const double cl = __dmul_rn(Ak[l * n_k], h_k);
@@ -608,14 +623,13 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
                 const double mu = owned ? ps[Ph::OFF_WFN + NY + j]
-                    * lam[co + (i64)NY * (N - 1) + (i64)j * N + m] : 0.0;
+                    * (ml == tid ? lam_p[j] : lam[co + (i64)NY * (N - 1) + (i64)j * N + m]) : 0.0;
                 muh[NY + j] = mu;
                 mut[NY + j] = 0.0;
             }
 #pragma unroll
             for (int i = 0; i < NQ; ++i) {
-                const double mu = -ps[Ph::OFF_WFN + NY + NP + i]
-                    * lam[co + (i64)NY * (N - 1) + (i64)NP * N + i] * wq;
+                const double mu = -ps[Ph::OFF_WFN + NY + NP + i] * lam_q[i] * wq;
                 mut[NY + NP + i] = mu;
                 muh[NY + NP + i] = hp * mu;
             }
@@ -701,7 +715,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
             const int l = r - b;
             const int n_k = sSecOrder[s + 1];
             const double h_k = sHk[s + 1];
-            const double* Arow = sB + p.order_a_off[n_k] + l * n_k;
+            const double* Arow = sB + sAoff[s + 1] + l * n_k;
             if (NEED_SF) {
 #pragma unroll
                 for (int i = 0; i < NY; ++i) {

@@ -262,7 +262,7 @@ def smem_bytes(S, layouts, threads):
         dbl = (len(S.btab) + SS + 1 + (pd.NY + len(pd.d1v) + nds) * (NN | 1)
                + len(pd.d1v) * (SS + 1)
                + pd.NY * (NN + 16) + threads // 32 + 2)
-        ints = (SS + 2) + (SS + 1) + NN + 8
+        ints = (SS + 2) + (SS + 1) + NN + 2 * (SS + 1) + 8
         best = max(best, 8 * dbl + 4 * ints)
     best = max(best, 8 * (32 + S.bv_size))      # border pass: scratch + BV
     return int((best + 15) // 16 * 16)
