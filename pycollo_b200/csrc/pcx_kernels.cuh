@@ -486,6 +486,28 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         for (int m = 0; m < n - 1; ++m) sNodeSec[b + m] = s;
         if (s == nsec - 1) sNodeSec[b + n - 1] = s;
     }
+    __syncthreads();
+    // ---- this thread's node, as far as the tables know it (a tile never holds
+    // more nodes than the CTA has threads): its section, position, section
+    // lengths and quadrature weight are all formed before the dependency wait
+    const int ml = tid;
+    const bool active = ml < nn;
+    const int s = active ? sNodeSec[ml] : 0;
+    const int mloc = ml - sSecNode[s + 1];
+    const int n_k = sSecOrder[s + 1];
+    const double h_k = sHk[s + 1];
+    const bool start_with_prev = active && (mloc == 0) && (s > 0 || has_prev);
+    const int n_pr = start_with_prev ? sSecOrder[s] : 0;
+    const double h_pr = start_with_prev ? sHk[s] : 0.0;
+    const int a_k = sAoff[s + 1] + mloc, a_pr = sAoff[s] + n_pr - 1;
+    const int lrow_k = prev_rows + sSecNode[s + 1], lrow_pr = prev_rows + sSecNode[s];
+    // quadrature weight of this node, accumulated as pycollo/mesh.py:325-326
+    double wq = 0.0;
+    if (NQ > 0 && (WANT_C || WANT_G || WANT_H)) {
+        if (start_with_prev)
+            wq = __dmul_rn(sB[sWoff[s] + n_pr - 1], h_pr);
+        wq = __dadd_rn(wq, __dmul_rn(sB[sWoff[s + 1] + mloc], h_k));
+    }
     // the scatter's tables (run descriptor -> type -> recipe word -> slot base) are
     // a chain of dependent loads: walked here, in the shadow of the previous
     // kernel, instead of between the node phase and the first store
@@ -562,32 +584,16 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     double* bv = p.bv + (i64)inst * p.bv_size;
 
     // ---- node-parallel evaluation ---------------------------------------------
-    for (int ml = tid; ml < nn; ml += T) {
+    if (active) {
         const bool owned = (ml < nn - 1) || last_tile;
-        const int s = sNodeSec[ml];
-        const int mloc = ml - sSecNode[s + 1];
-        const int n_k = sSecOrder[s + 1];
-        const double h_k = sHk[s + 1];
         const i64 m = node0 + ml;
-        const bool start_with_prev = (mloc == 0) && (s > 0 || has_prev);
-        const int n_pr = start_with_prev ? sSecOrder[s] : 0;
-        const double h_pr = start_with_prev ? sHk[s] : 0.0;
 
         double v[NV + NS > 0 ? NV + NS : 1];
 #pragma unroll
         for (int a = 0; a < NV; ++a)
-            v[a] = pcx_unscale(ps[Ph::OFF_VV + a],
-                               ml == tid ? xt0[a] : x[xo + (i64)a * N + m], ps[Ph::OFF_RV + a]);
+            v[a] = pcx_unscale(ps[Ph::OFF_VV + a], xt0[a], ps[Ph::OFF_RV + a]);
 #pragma unroll
         for (int j = 0; j < NS; ++j) v[NV + j] = sv[j];
-
-        // quadrature weight of this node, accumulated as pycollo/mesh.py:325-326
-        double wq = 0.0;
-        if (NQ > 0 && (WANT_C || WANT_G || WANT_H)) {
-            if (start_with_prev)
-                wq = __dmul_rn(sB[sWoff[s] + n_pr - 1], h_pr);
-            wq = __dadd_rn(wq, __dmul_rn(sB[sWoff[s + 1] + mloc], h_k));
-        }
 
         double muh[NF > 0 ? NF : 1], mut[NF > 0 ? NF : 1];
 #pragma unroll
@@ -597,8 +603,8 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
 #pragma unroll
             for (int i = 0; i < NY; ++i) lacc[i] = 0.0;
             if (start_with_prev) {
-                const double* Apr = sB + sAoff[s] + n_pr - 1;
-                const double* lrow = sLam + prev_rows + sSecNode[s];
+                const double* Apr = sB + a_pr;
+                const double* lrow = sLam + lrow_pr;
                 for (int l = 0; l < n_pr - 1; ++l) {
                     const double cl = __dmul_rn(Apr[l * n_pr], h_pr);
 #pragma unroll
@@ -606,8 +612,8 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
                 }
             }
             if (owned) {
-                const double* Ak = sB + sAoff[s + 1] + mloc;
-                const double* lrow = sLam + prev_rows + sSecNode[s + 1];
+                const double* Ak = sB + a_k;
+                const double* lrow = sLam + lrow_k;
                 for (int l = 0; l < n_k - 1; ++l) {
                     const double cl = __dmul_rn(Ak[l * n_k], h_k);
 #pragma unroll
@@ -623,7 +629,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
                 const double mu = owned ? ps[Ph::OFF_WFN + NY + j]
-                    * (ml == tid ? lam_p[j] : lam[co + (i64)NY * (N - 1) + (i64)j * N + m]) : 0.0;
+                    * lam_p[j] : 0.0;
                 muh[NY + j] = mu;
                 mut[NY + j] = 0.0;
             }

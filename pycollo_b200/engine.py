@@ -288,6 +288,9 @@ class Engine:
         self.device = int(device)
         self.threads = int(S.threads)
         self.tables = build_tables(S, layouts)
+        if S.max_tile_nodes > self.threads:
+            raise PcxError(f"a tile holds {S.max_tile_nodes} nodes but the CTA has only "
+                           f"{self.threads} threads (one thread per node)")
         self.smem = smem_bytes(S, layouts, self.threads)
         if self.smem > 227 * 1024:
             raise PcxError(f"tile needs {self.smem} B of shared memory (> 227 KB)")
