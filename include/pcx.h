@@ -145,6 +145,20 @@ int pcx_eval_jac_hess(pcx_engine* e, const double* x, const double* lam,
  * calls pcx_apply_border (stage 2), which writes the O(1) border slots
  * (integral/endpoint rows, q/t/s corner, J, gradient entries).              */
 int pcx_set_shard(pcx_engine* e, int tile_begin, int tile_end);
+/* Fused variant: no NCCL call and no second launch.  The border rank allocates
+ * the exchange buffer (pcx_exchange_alloc; `handle` is its CUDA IPC handle, 64
+ * bytes, to be sent to the other ranks by any means), every rank attaches
+ * (pcx_exchange_attach; the border rank and same-process users pass NULL / use
+ * _attach_ptr).  From then on pcx_eval on a sharded engine writes the rank's
+ * share of the border values straight into the border rank's memory over NVLink
+ * (system-scope release), and the border rank's kernel waits for all shares,
+ * sums them in rank order and writes the border slots itself.  All ranks must
+ * call pcx_eval the same number of times (an epoch counter pairs the calls).   */
+int pcx_exchange_alloc(pcx_engine* e, int world, unsigned char handle[64]);
+int pcx_exchange_attach(pcx_engine* e, int rank, int world, int border_rank,
+                        const unsigned char handle[64]);
+int pcx_exchange_attach_ptr(pcx_engine* e, int rank, int world, int border_rank, void* base);
+int pcx_exchange_buffer(pcx_engine* e, void** base);
 int pcx_shard_buffer(pcx_engine* e, double** xbuf, int64_t* n);
 int pcx_apply_border(pcx_engine* e, int what, const double* x, const double* lam,
                      const double* sigma, double* f, double* grad, double* c,

@@ -895,7 +895,8 @@ __device__ __noinline__ void pcx_border(const PcxParams& p, const int inst, doub
     const int mode = p.border_mode;
     const int xlen = (PCX_BV_PTVAL - 1) + (p.bv_size - PCX_BV_IRR);
     double* xb = p.xbuf + (i64)inst * xlen;
-    if (mode != 1) pcx_border_map(p, inst, bv, sRS, false, scratch + 31);   // warm the map tables
+    if (mode != 1 && (mode != 3 || p.rank == p.border_rank))
+        pcx_border_map(p, inst, bv, sRS, false, scratch + 31);   // warm the map tables
 
     if (mode == 2) {
         // stage 2 of a sharded evaluation: reductions and end-node values come
@@ -951,6 +952,40 @@ __device__ __noinline__ void pcx_border(const PcxParams& p, const int inst, doub
         for (int i = 1 + tid; i < PCX_BV_PTVAL; i += T) xb[i - 1] = bv[i];
         for (int i = PCX_BV_IRR + tid; i < p.bv_size; i += T)
             xb[(PCX_BV_PTVAL - 1) + (i - PCX_BV_IRR)] = bv[i];
+    } else if (mode == 3) {
+        // fused exchange over peer memory: write this rank's share into the
+        // border rank's buffer, make it visible system-wide, publish the epoch
+        double* mine = p.peer_xbuf + ((i64)p.rank * p.batch + inst) * p.bv_size;
+        for (int i = 1 + tid; i < PCX_BV_PTVAL; i += T) mine[i - 1] = bv[i];
+        for (int i = PCX_BV_IRR + tid; i < p.bv_size; i += T)
+            mine[(PCX_BV_PTVAL - 1) + (i - PCX_BV_IRR)] = bv[i];
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0)
+            asm volatile("st.release.sys.global.u64 [%0], %1;"
+                         :: "l"(p.peer_flags + (i64)p.rank * p.batch + inst), "l"(p.epoch) : "memory");
+        if (p.rank == p.border_rank) {
+            // wait for every rank's share of this evaluation, then sum in rank
+            // order (deterministic) and apply the border map
+            if (tid < p.world) {
+                unsigned long long seen;
+                do {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];"
+                                 : "=l"(seen) : "l"(p.peer_flags + (i64)tid * p.batch + inst) : "memory");
+                    if (seen < p.epoch) __nanosleep(200);
+                } while (seen < p.epoch);
+            }
+            __syncthreads();
+            for (int i = tid; i < xlen; i += T) {
+                double acc = 0.0;
+                for (int r = 0; r < p.world; ++r)
+                    acc += __ldcv(p.peer_xbuf + ((i64)r * p.batch + inst) * p.bv_size + i);
+                const int j = i < PCX_BV_PTVAL - 1 ? 1 + i : PCX_BV_IRR + (i - (PCX_BV_PTVAL - 1));
+                bv[j] = acc;
+            }
+            __syncthreads();
+            pcx_border_map(p, inst, bv, sRS, true, nullptr);
+        }
     } else {
         pcx_border_map(p, inst, bv, sRS, true, nullptr);
     }

@@ -45,6 +45,14 @@ struct PcxParams {
     // (stage 1); 2: border CTA only, reads the all-reduced xbuf (stage 2)
     int tile_begin, tile_count, border_mode;
     double* xbuf;           // (batch, xbuf_len): [reductions | end-node values]
+    // border_mode 3: the exchange is fused into the kernel over peer memory
+    // (NVLink).  Every rank's border CTA writes its share into slot `rank` of
+    // peer_xbuf (world x batch x bv_size doubles, in the border rank's memory)
+    // and then publishes `epoch` in peer_flags[rank]; the border rank waits for
+    // all flags, sums the shares in rank order and applies the border map.
+    double* peer_xbuf; unsigned long long* peer_flags;
+    unsigned long long epoch;
+    int rank, world, border_rank, pad1;
     // tiles
     const i64* tile_desc;   // 8 per tile: phase,k0,k1,node0,nn,run0,run1,-
     const int* run_slo; const int* run_shi; const int* run_type;

@@ -86,6 +86,10 @@ def load_library(rebuild=False):
     lib.pcx_synchronize.argtypes = [vp, vp]
     lib.pcx_flush_l2.argtypes = [vp, i64, vp]
     lib.pcx_set_shard.argtypes = [vp, i32, i32]
+    lib.pcx_exchange_alloc.argtypes = [vp, i32, ctypes.c_char_p]
+    lib.pcx_exchange_attach.argtypes = [vp, i32, i32, i32, ctypes.c_char_p]
+    lib.pcx_exchange_attach_ptr.argtypes = [vp, i32, i32, i32, vp]
+    lib.pcx_exchange_buffer.argtypes = [vp, ctypes.POINTER(vp)]
     lib.pcx_shard_buffer.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
     lib.pcx_apply_border.argtypes = [vp, i32, dp, dp, dp, dp, dp, dp, dp, dp, vp]
     lib.pcx_interp_guess.argtypes = [vp, dp, dp, dp, dp, dp, i32, vp]
@@ -382,6 +386,27 @@ class Engine:
     def set_shard(self, tile_begin, tile_end):
         self._check(self.lib.pcx_set_shard(self.h, int(tile_begin), int(tile_end)),
                     "pcx_set_shard")
+
+    def exchange_alloc(self, world):
+        """Border rank: allocate the peer-memory exchange buffer; returns its CUDA
+        IPC handle (64 bytes) for the other ranks."""
+        buf = ctypes.create_string_buffer(64)
+        self._check(self.lib.pcx_exchange_alloc(self.h, int(world), buf), "pcx_exchange_alloc")
+        return buf.raw
+
+    def exchange_attach(self, rank, world, border_rank, handle=None):
+        self._check(self.lib.pcx_exchange_attach(self.h, int(rank), int(world), int(border_rank),
+                                                 handle), "pcx_exchange_attach")
+
+    def exchange_attach_ptr(self, rank, world, border_rank, base):
+        self._check(self.lib.pcx_exchange_attach_ptr(self.h, int(rank), int(world),
+                                                     int(border_rank), ctypes.c_void_p(base)),
+                    "pcx_exchange_attach_ptr")
+
+    def exchange_buffer(self):
+        ptr = ctypes.c_void_p()
+        self._check(self.lib.pcx_exchange_buffer(self.h, ctypes.byref(ptr)), "pcx_exchange_buffer")
+        return int(ptr.value)
 
     def shard_buffer(self):
         """(device pointer, length) of the small border-exchange buffer."""

@@ -105,7 +105,7 @@ class MeshSharder:
     exactly one writer); with ``border_rank=None`` every rank writes them.
     """
 
-    def __init__(self, engine, world_size=None, rank=None, border_rank=None):
+    def __init__(self, engine, world_size=None, rank=None, border_rank=None, fused=False):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -116,10 +116,21 @@ class MeshSharder:
         self.world_size, self.rank = int(world_size), int(rank)
         self.engine = engine
         self.border_rank = border_rank
+        self.fused = bool(fused) and self.world_size > 1
         self.lo, self.hi = shard_range(engine.S.num_tiles, self.world_size, self.rank)
         engine.set_shard(self.lo, self.hi)
         ptr, n = engine.shard_buffer()
         self.xbuf = torch.as_tensor(_DeviceArray(ptr, n), device=f"cuda:{engine.device}")
+        if self.fused:
+            # exchange fused into the kernel over peer memory (NVLink): the border
+            # rank owns the buffer, the others map it through CUDA IPC
+            br = 0 if border_rank is None else int(border_rank)
+            self.border_rank = br
+            box = [engine.exchange_alloc(self.world_size) if self.rank == br else None]
+            dist.broadcast_object_list(box, src=br)
+            engine.exchange_attach(self.rank, self.world_size, br,
+                                   None if self.rank == br else box[0])
+            dist.barrier()
 
     def evaluate(self, what, x, lam=None, sigma=None, f=None, grad=None, c=None, dy=None,
                  jac=None, hess=None):
@@ -128,8 +139,8 @@ class MeshSharder:
         st = self.torch.cuda.current_stream().cuda_stream
         self.engine.eval_ptr(what, x, lam=lam, sigma=sigma, f=f, grad=grad, c=c, dy=dy,
                              jac=jac, hess=hess, stream=st)
-        if self.world_size == 1:
-            return                       # unsharded engine: pcx_eval did the border pass
+        if self.world_size == 1 or self.fused:
+            return     # unsharded: pcx_eval did the border pass; fused: the kernel exchanged
         self.dist.all_reduce(self.xbuf)
         if self.border_rank is None or self.border_rank == self.rank:
             self.engine.apply_border(what, x, lam=lam, sigma=sigma, f=f, grad=grad, c=c,

@@ -162,3 +162,40 @@ def test_gpu_two_stage_sharded_evaluation(problem, K, nodes, kw):
         assert max_err(out["jac"].cpu().numpy(), B.G_nonzeros(xn)) <= 1e-12
         assert max_err(out["hess"].cpu().numpy(), B.H_nonzeros(xn, 0.7, ln)) <= 1e-12
         assert max_err(out["c"].cpu().numpy(), B.c(xn)) <= 1e-12
+
+
+@pytest.mark.gpu
+def test_gpu_fused_peer_exchange_same_device():
+    """border_mode 3 (exchange fused into the kernel over peer memory) with three
+    "ranks" on one device sharing one exchange buffer: the non-border ranks run
+    first on the stream, the border rank last (it waits for their shares)."""
+    low, B, scal = build_case(examples.multiphase_sliding_mass(), "lobatto", 6, [4, 3, 5, 4, 6, 3],
+                              None, seed=3, max_tile_nodes=8)
+    S = low.S
+    what = E.EVAL_C | E.EVAL_JAC | E.EVAL_HESS | E.EVAL_F | E.EVAL_GRAD
+    rng = np.random.default_rng(4)
+    world = 3
+    engines = []
+    for r in range(world):
+        eng = E.Engine(S, low.layouts, low.header)
+        eng.set_scaling(*scal)
+        eng.set_shard(*shard_range(S.num_tiles, world, r))
+        engines.append(eng)
+    engines[0].exchange_alloc(world)
+    base = engines[0].exchange_buffer()
+    for r, eng in enumerate(engines):
+        eng.exchange_attach_ptr(r, world, 0, base)
+    z = lambda n: torch.zeros(n, dtype=torch.float64, device="cuda")
+    for trial in range(3):                                   # epochs pair the calls
+        xn, ln = rng.uniform(-0.5, 0.5, S.num_x), rng.standard_normal(S.num_c)
+        x, lam = torch.from_numpy(xn).cuda(), torch.from_numpy(ln).cuda()
+        sig = torch.tensor([0.7], dtype=torch.float64, device="cuda")
+        out = dict(f=z(1), grad=z(S.num_x), c=z(S.num_c), jac=z(S.nnz_g), hess=z(S.nnz_h))
+        for r in (2, 1, 0):
+            engines[r].eval_ptr(what, x, lam=lam, sigma=sig, **out)
+        torch.cuda.synchronize()
+        assert max_err(out["jac"].cpu().numpy(), B.G_nonzeros(xn)) <= 1e-12
+        assert max_err(out["hess"].cpu().numpy(), B.H_nonzeros(xn, 0.7, ln)) <= 1e-12
+        assert max_err(out["c"].cpu().numpy(), B.c(xn)) <= 1e-12
+        assert max_err(out["grad"].cpu().numpy(), B.g(xn)) <= 1e-12
+        assert max_err(out["f"].cpu().numpy(), [B.J(xn)]) <= 1e-12

@@ -16,6 +16,7 @@ from pycollo_b200.parallel import MeshSharder
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 83333          # x3 nodes x4 phases ~ 10^6 nodes
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+fused = len(sys.argv) > 3 and sys.argv[3] == "fused"
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -37,7 +38,7 @@ st = torch.cuda.current_stream().cuda_stream
 eng.eval_ptr(what, x, lam=lam, jac=jac[1], hess=hes[1], stream=st)
 torch.cuda.synchronize()
 ref_j, ref_h = jac[1].clone(), hes[1].clone()
-sh = MeshSharder(eng, world, rank, border_rank=0)
+sh = MeshSharder(eng, world, rank, border_rank=0, fused=fused)
 jac[0].zero_(); hes[0].zero_()
 sh.evaluate(what, x, lam=lam, jac=jac[0], hess=hes[0])
 if world > 1:
@@ -61,7 +62,7 @@ if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
     alg = 8 * (S.num_x + S.nnz_g) + 8 * (S.num_x + S.num_c + S.nnz_h)
-    print(json.dumps(dict(workload="delta_iii 4 phases", nodes=int(sum(t.N for t in S.ph)), n_gpus=world,
+    print(json.dumps(dict(workload="delta_iii 4 phases", exchange="fused peer-memory" if fused and world > 1 else "nccl all_reduce + 2nd launch", nodes=int(sum(t.N for t in S.ph)), n_gpus=world,
                           num_x=S.num_x, nnz_G=S.nnz_g, nnz_H=S.nnz_h, tiles=S.num_tiles,
                           rel_err_jac=ej, rel_err_hess=eh, ms_per_eval=round(float(ms), 4),
                           evals_per_s=round(1e3 / float(ms), 1),
