@@ -5,7 +5,9 @@
 // the per-node expression bodies + constexpr dimension/offset tables, emitted by
 // pycollo_b200/codegen.py).  Everything else -- tiling, shared-memory staging,
 // the collocation contractions, the coalesced scatter into the fixed CCS
-// pattern, warp-shuffle reductions and the last-CTA border pass -- is below.
+// pattern, warp-shuffle reductions, the dedicated border CTA, the programmatic
+// dependent launch protocol and the multi-GPU border exchange over peer memory
+// -- is below.
 //
 // One CTA = one tile = a contiguous range of mesh sections of one phase
 // (pycollo_b200/structure.py).  One launch evaluates any subset of
@@ -75,8 +77,6 @@ __device__ __forceinline__ double pcx_block_sum(double v, double* scratch) {
     }
     return r;   // valid on thread 0
 }
-
-template <int N> struct PcxArr { double v[N > 0 ? N : 1]; };
 
 #ifdef PCX_DEBUG_TIMELINE
 // per-CTA phase timestamps (ns) into the partials scratch, 16 slots per tile
