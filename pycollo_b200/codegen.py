@@ -35,7 +35,7 @@ class _CudaPrinter(C99CodePrinter):
 
     def _print_Pow(self, expr):
         base, exp = expr.base, expr.exp
-        if exp.is_Integer and 1 <= abs(int(exp)) <= 4:
+        if exp.is_Integer and 1 <= abs(int(exp)) <= 12:
             b = self.parenthesize(base, 1000)
             prod = "*".join([b] * abs(int(exp)))
             return f"({prod})" if int(exp) > 0 else f"(1.0/({prod}))"
@@ -103,6 +103,31 @@ def _share_reciprocals(repl, reduced):
     return out, reduced
 
 
+def _share_half_powers(repl, reduced):
+    """``b**(p/2)`` with odd p becomes ``sqrt(b)**p`` with one shared ``sqrt(b)``
+    per base: an fp64 ``pow`` is a few hundred instructions, a square root ~30, and
+    gravity / drag terms are full of ``r**(-3/2)``, ``r**(-5/2)``, ``v**(3/2)``.
+    Negative powers are then turned into one reciprocal by ``_share_reciprocals``."""
+    roots, out = {}, []
+
+    def fix(e):
+        for pw in sorted((q for q in e.atoms(sym.Pow)
+                          if q.exp.is_Rational and q.exp.q == 2 and abs(q.exp.p) >= 3),
+                         key=sym.default_sort_key):
+            b = pw.base
+            if b not in roots:
+                r = sym.Symbol(f"sq_{len(roots)}", positive=True)
+                out.append((r, sym.sqrt(b)))
+                roots[b] = r
+            e = e.xreplace({pw: roots[b] ** int(pw.exp.p)})
+        return e
+
+    for s_, e in repl:
+        out.append((s_, fix(e)))
+    reduced = [fix(e) for e in reduced]
+    return out, reduced
+
+
 def _emit_program(inputs, outputs, indent="        "):
     """Straight-line program: ``inputs`` = [(symbol, c_expr)], ``outputs`` =
     [(c_lvalue, sympy expr)].  Shared CSE across all outputs; sin/cos of the
@@ -135,6 +160,7 @@ def _emit_program(inputs, outputs, indent="        "):
         exprs = [e.xreplace(trig_sub) for e in exprs]
     repl, reduced = sym.cse(exprs, symbols=sym.numbered_symbols("w_"),
                             order="none")
+    repl, reduced = _share_half_powers(repl, reduced)
     repl, reduced = _share_reciprocals(repl, reduced)
     for s, cexpr in inputs:
         lines.append(f"{indent}const double {s} = {cexpr};")
