@@ -36,8 +36,63 @@ class NlpCallbacks:
             self._h_struct = (hr, hc)
         else:
             raise ValueError("ordering must be 'cyipopt' or 'casadi'")
+        self.ordering = ordering
         self.num_evals = dict(objective=0, gradient=0, constraints=0,
                               jacobian=0, hessian=0)
+        self._fast = None
+
+    # -- the hot callbacks: pinned staging, device-side permutation ------------
+    def _fast_path(self):
+        """Persistent buffers for ``jacobian`` / ``hessian``: pinned host staging for
+        x, lam and the values (copies at PCIe speed instead of pageable-memory
+        speed), and the cyipopt permutation applied on the device (``pcx_gather``)
+        instead of a 4-million-element numpy fancy index per call."""
+        if self._fast is None:
+            import torch
+            it = self.it
+            S = it.S
+            eng = it.create_engine()
+            dev = torch.device("cuda", it.device)
+            f64 = dict(dtype=torch.float64)
+            b = dict(
+                torch=torch, eng=eng, stream=torch.cuda.Stream(device=dev),
+                hx=torch.empty(S.num_x, **f64).pin_memory(), dx=torch.empty(S.num_x, device=dev, **f64),
+                hl=torch.empty(S.num_c, **f64).pin_memory(), dl=torch.empty(S.num_c, device=dev, **f64),
+                ds=torch.ones(1, device=dev, **f64), hs=torch.ones(1, **f64).pin_memory(),
+                dg=torch.empty(S.nnz_g, device=dev, **f64), dgp=torch.empty(S.nnz_g, device=dev, **f64),
+                hg=torch.empty(S.nnz_g, **f64).pin_memory(),
+                dh=torch.empty(S.nnz_h, device=dev, **f64), dhp=torch.empty(S.nnz_h, device=dev, **f64),
+                hh=torch.empty(S.nnz_h, **f64).pin_memory(),
+                gperm=torch.from_numpy(np.ascontiguousarray(self.g_perm, dtype=np.int64)).to(dev),
+                hperm=torch.from_numpy(np.ascontiguousarray(self.h_perm, dtype=np.int64)).to(dev))
+            self._fast = b
+        return self._fast
+
+    def _values(self, what, x, lagrange=None, obj_factor=1.0):
+        b = self._fast_path()
+        torch, eng, st = b["torch"], b["eng"], b["stream"]
+        jac = what == _engine.EVAL_JAC
+        b["hx"].numpy()[:] = x
+        with torch.cuda.stream(st):
+            b["dx"].copy_(b["hx"], non_blocking=True)
+            if not jac:
+                b["hl"].numpy()[:] = lagrange
+                b["hs"][0] = float(obj_factor)
+                b["dl"].copy_(b["hl"], non_blocking=True)
+                b["ds"].copy_(b["hs"], non_blocking=True)
+            raw, perm, out, host = (b["dg"], b["gperm"], b["dgp"], b["hg"]) if jac else \
+                (b["dh"], b["hperm"], b["dhp"], b["hh"])
+            if jac:
+                eng.eval_ptr(what, b["dx"], jac=raw, stream=st.cuda_stream)
+            else:
+                eng.eval_ptr(what, b["dx"], lam=b["dl"], sigma=b["ds"], hess=raw, stream=st.cuda_stream)
+            if self.ordering == "cyipopt":
+                eng.gather(raw, perm, raw.numel(), out, stream=st.cuda_stream)
+            else:
+                out = raw
+            host.copy_(out, non_blocking=True)
+        st.synchronize()
+        return host.numpy()          # pinned staging: valid until the next call of this kind
 
     def objective(self, x):
         self.num_evals["objective"] += 1
@@ -53,15 +108,14 @@ class NlpCallbacks:
 
     def jacobian(self, x):
         self.num_evals["jacobian"] += 1
-        return self.it.evaluate(_engine.EVAL_JAC, x)["jac"][0][self.g_perm]
+        return self._values(_engine.EVAL_JAC, x)
 
     def jacobianstructure(self):
         return self._g_struct
 
     def hessian(self, x, lagrange, obj_factor):
         self.num_evals["hessian"] += 1
-        return self.it.evaluate(_engine.EVAL_HESS, x, lagrange,
-                                obj_factor)["hess"][0][self.h_perm]
+        return self._values(_engine.EVAL_HESS, x, lagrange, obj_factor)
 
     def hessianstructure(self):
         return self._h_struct
