@@ -72,3 +72,43 @@ def max_err(a, b):
     assert np.all(np.isfinite(a)), f"{np.sum(~np.isfinite(a))} non-finite values"
     scale = max(1.0, float(np.max(np.abs(b)))) * 1e-2
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), scale)))
+
+
+def cpu_mesh_error_chain(ocp, low, low_ph, mesh, ph, xh, dyh):
+    """CPU chain of the reference's mesh-error algorithm (oracle/mesh_error.py:
+    numpy polynomial fits per state and section, then the error loops) for a
+    solution ``xh`` / ``dyh`` on ``mesh``; returns the largest relative error.
+    Used by tests and by tools/mesh_error_bench.py as the timed CPU leg."""
+    from oracle import mesh_error as OM
+    from oracle.blockwise import BlockwiseNLP
+    S = low.S
+    B = BlockwiseNLP(ocp, low_ph.ir.full_bounds,
+                     [dict(N=m.N, sI=m.sI_matrix, sA=m.sA_matrix, W=m.W_matrix) for m in ph.p],
+                     scaling_method="none")
+    sI = [m.sI_matrix for m in ph.p]
+    xs, Ts = [], []
+    for ip, (irp, t) in enumerate(zip(low.ir.phases, S.ph)):
+        ny, nu, N = irp.n_y, irp.n_u, t.N
+        y = xh[t.x_off:t.x_off + ny * N].reshape(ny, N)
+        u = xh[t.x_off + ny * N:t.x_off + (ny + nu) * N].reshape(nu, N)
+        d = dyh[t.dy_off:t.dy_off + ny * N].reshape(ny, N)
+        tv = xh[t.q_col + irp.n_q:t.q_col + irp.n_q + irp.n_t]
+        T = (tv[-1] if irp.t_needed[1] else float(irp.tF)) - (tv[0] if irp.t_needed[0] else float(irp.t0))
+        Ts.append(T)
+        bnd, bph = mesh.mesh_index_boundaries[ip], ph.mesh_index_boundaries[ip]
+        yp, up = OM.fit_section_polys(mesh.tau[ip], y, d, u, T, bnd, mesh.N_K[ip])
+        y_ph = OM.interpolate_to_ph(y, yp, bnd, bph, ph.tau[ip])
+        u_ph = OM.interpolate_to_ph(u, up, bnd, bph, ph.tau[ip])
+        xs += [y_ph.ravel(), u_ph.ravel(), xh[t.q_col:t.q_col + irp.n_q + irp.n_t]]
+    xs.append(xh[S.s_off:])
+    x_ph = np.concatenate(xs)
+    dyp = B.dy(x_ph)
+    o, worst = 0, 0.0
+    for ip, (irp, t) in enumerate(zip(low.ir.phases, low_ph.S.ph)):
+        ny, Nph = irp.n_y, t.N
+        y_ph = x_ph[t.x_off:t.x_off + ny * Nph].reshape(ny, Nph)
+        _, _, m = OM.phase_mesh_error(dyp[o:o + ny * Nph], y_ph, sI[ip], 0.5 * Ts[ip], ph.N_K[ip],
+                                      ph.mesh_index_boundaries[ip])
+        o += ny * Nph
+        worst = max(worst, float(m.max()))
+    return worst

@@ -49,40 +49,10 @@ def run(problem, K, nodes, cpu=True, steps=30):
     out = dict(problem=problem, sections=K, nodes=int(sum(m.N for m in mesh.p)),
                ph_nodes=int(sum(m.N for m in ev.ph_mesh.p)), gpu_us=round(us, 1))
     if cpu:
-        from oracle import mesh_error as OM
-        from oracle.blockwise import BlockwiseNLP
+        from helpers import cpu_mesh_error_chain          # tests/: the only home of oracle imports
         xh, dyh = x.cpu().numpy(), dy.cpu().numpy()
-        ph = ev.ph_mesh
-        B = BlockwiseNLP(ocp, ev.low.ir.full_bounds,
-                         [dict(N=m.N, sI=m.sI_matrix, sA=m.sA_matrix, W=m.W_matrix) for m in ph.p],
-                         scaling_method="none")
-        sI = [m.sI_matrix for m in ph.p]
         t0 = time.perf_counter()
-        xs = []
-        for ip, (irp, t) in enumerate(zip(low.ir.phases, S.ph)):
-            ny, nu, N = irp.n_y, irp.n_u, t.N
-            y = xh[t.x_off:t.x_off + ny * N].reshape(ny, N)
-            u = xh[t.x_off + ny * N:t.x_off + (ny + nu) * N].reshape(nu, N)
-            d = dyh[t.dy_off:t.dy_off + ny * N].reshape(ny, N)
-            tv = xh[t.q_col + irp.n_q:t.q_col + irp.n_q + irp.n_t]
-            T = (tv[-1] if irp.t_needed[1] else float(irp.tF)) - (tv[0] if irp.t_needed[0] else float(irp.t0))
-            bnd, bph = mesh.mesh_index_boundaries[ip], ph.mesh_index_boundaries[ip]
-            yp, up = OM.fit_section_polys(mesh.tau[ip], y, d, u, T, bnd, mesh.N_K[ip])
-            y_ph = OM.interpolate_to_ph(y, yp, bnd, bph, ph.tau[ip])
-            u_ph = OM.interpolate_to_ph(u, up, bnd, bph, ph.tau[ip])
-            xs += [y_ph.ravel(), u_ph.ravel(), xh[t.q_col:t.q_col + irp.n_q + irp.n_t]]
-        xs.append(xh[S.s_off:])
-        x_ph = np.concatenate(xs)
-        dyp = B.dy(x_ph)
-        o = 0
-        worst = 0.0
-        for ip, (irp, t) in enumerate(zip(low.ir.phases, ev.low.S.ph)):
-            ny, Nph = irp.n_y, t.N
-            y_ph = x_ph[t.x_off:t.x_off + ny * Nph].reshape(ny, Nph)
-            a, r, m = OM.phase_mesh_error(dyp[o:o + ny * Nph], y_ph, sI[ip], 0.5 * T, ph.N_K[ip],
-                                          ph.mesh_index_boundaries[ip])
-            o += ny * Nph
-            worst = max(worst, float(m.max()))
+        worst = cpu_mesh_error_chain(ocp, low, ev.low, mesh, ev.ph_mesh, xh, dyh)
         out["cpu_ms"] = round(1e3 * (time.perf_counter() - t0), 1)
         out["speedup"] = round(out["cpu_ms"] * 1e3 / us)
         out["max_rel_err_gpu_vs_cpu"] = float(abs(worst - float(mx.max())))
