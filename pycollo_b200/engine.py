@@ -330,10 +330,9 @@ class Engine:
         if min_blocks is None and "PCX_MIN_BLOCKS" in os.environ:
             min_blocks = int(os.environ["PCX_MIN_BLOCKS"])
         if min_blocks is None:
-            from .structure import RESIDENT_CTAS
+            from .structure import resident_ctas
             per_sm = -(-S.num_tiles * 1 // 148)
-            min_blocks = max(1, min(RESIDENT_CTAS, per_sm)) if S.threads <= 128 else \
-                max(1, min(3, per_sm))
+            min_blocks = max(1, min(resident_ctas(S.threads), per_sm))
         return int(min_blocks)
 
     def __del__(self):

@@ -28,6 +28,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
+import os
+
 import numpy as np
 
 # recipe word bit layout (must match csrc/pcx_kernels.cuh)
@@ -44,6 +46,12 @@ RC_LOCAL_SHIFT = 40                           # slot inside the variable's perio
 
 # CTAs the kernels are compiled to keep resident per SM on large meshes
 RESIDENT_CTAS = 6
+LARGE_MESH_THREADS = 128
+
+
+def resident_ctas(threads):
+    """CTAs per SM the tiling and the register cap aim at: 24 warps per SM."""
+    return {160: 5, 192: 4, 256: 3}.get(int(threads), RESIDENT_CTAS if threads <= 128 else 3)
 
 # border-map groups
 GRP_C, GRP_G, GRP_H, GRP_J, GRP_GRAD = 0, 1, 2, 3, 4
@@ -139,7 +147,8 @@ class NLPStructure:
             # CTA size: one thread per node of a tile; small problems (multi-start
             # sweeps of ~31-node meshes) get a CTA no wider than their mesh
             nmax = max(int(m.N) for m in meshes)
-            threads = 32 if nmax <= 32 else (64 if nmax <= 64 else 128)
+            threads = 32 if nmax <= 32 else (64 if nmax <= 64 else
+                                             int(os.environ.get("PCX_THREADS", LARGE_MESH_THREADS)))
         self.threads = int(threads)
         self.P = len(ir.phases)
         self.NS = ir.n_s
@@ -721,8 +730,8 @@ class NLPStructure:
                 m = max(1, int(np.ceil(want / (sm_count * share))))
                 if tiles_per_sm:
                     m = max(m, int(tiles_per_sm))
-                elif m > RESIDENT_CTAS:
-                    m = -(-m // RESIDENT_CTAS) * RESIDENT_CTAS   # whole waves
+                elif m > resident_ctas(T):
+                    m = -(-m // resident_ctas(T)) * resident_ctas(T)   # whole waves
                 want = max(want, int(round(m * sm_count * share)))
             want = min(want, t.K)
             # the border pass is a CTA of its own (csrc/pcx_kernels.cuh): leave
