@@ -241,9 +241,13 @@ def run_cuda(args):
     hess = [torch.empty(S.nnz_h, dtype=torch.float64, device=dev) for _ in range(R)]
     stream = torch.cuda.current_stream().cuda_stream
 
+    # one pre-bound C-ABI call per ring slot: pcx_eval with its arguments converted
+    # once, as a compiled host would hold them
+    calls = [eng.bind(what, xs[k], lam=lams[k], jac=jacs[k], hess=hess[k], stream=stream)
+             for k in range(R)]
+
     def step(i):
-        k = i % R
-        eng.eval_ptr(what, xs[k], lam=lams[k], jac=jacs[k], hess=hess[k], stream=stream)
+        calls[i % R]()
 
     def barrier():
         if world > 1:

@@ -496,6 +496,23 @@ class Engine:
             _ptr(c), _ptr(dy), _ptr(jac), _ptr(hess), space,
             ctypes.c_void_p(stream) if stream else None), "pcx_eval")
 
+    def bind(self, what, x, lam=None, sigma=None, f=None, grad=None, c=None, dy=None,
+             jac=None, hess=None, space=PCX_DEVICE, stream=None):
+        """``pcx_eval`` with every argument converted once: returns a zero-argument
+        callable (one foreign call, ~2 us of host time instead of ~7 us through
+        ``eval_ptr``).  The buffers must stay alive and in place."""
+        args = (self.h, what, _ptr(x), _ptr(lam), _ptr(sigma), _ptr(f), _ptr(grad), _ptr(c),
+                _ptr(dy), _ptr(jac), _ptr(hess), space,
+                ctypes.c_void_p(stream) if stream else None)
+        fn, check = self.lib.pcx_eval, self._check
+
+        def call():
+            rc = fn(*args)
+            if rc:
+                check(rc, "pcx_eval")
+        call.keepalive = (x, lam, sigma, f, grad, c, dy, jac, hess)
+        return call
+
     def gather(self, src, perm, n, dst, stream=None):
         self._check(self.lib.pcx_gather(self.h, _ptr(src), _ptr(perm), n, _ptr(dst),
                                         PCX_DEVICE,
