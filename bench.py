@@ -19,6 +19,8 @@ One *step* = one evaluation of (G values, H values) for one synthetic iterate
   on a bounded sample of the same workload.  One thread is the reference's own
   degree of parallelism: its callbacks are CasADi SX virtual-machine evaluations,
   single-threaded by construction ("where time goes").
+  ``cpu_baseline.all_cores`` adds, for transparency, the aggregate rate of one such
+  single-threaded evaluation stream per host core (independent iterates).
 * ``amortised``: informational -- the same kernel with 8 iterates per launch.
 * ``--impl reference``: the reference's CPU implementation of this path.  The
   live reference (CasADi) cannot be installed here (no casadi/pyproprop wheel,
@@ -165,6 +167,65 @@ def batched_rate(low, scal, E, torch, dev, stream, alg_bytes, peak, batch=8, ste
     return {"batch_per_launch": batch, "us_per_eval": us, "evals_per_s": 1e6 / us,
             "achieved_GBs": gbs, "frac": gbs / peak,
             "note": "same kernel, 8 independent iterates per launch (grid.y); informational"}
+
+
+def _cpu_worker(seconds, q):
+    """One process of the all-cores CPU throughput leg: the oracle port on the same
+    workload, evaluations counted over a fixed wall-clock window."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("MKL_NUM_THREADS", "1")
+    from helpers import build_case
+    from pycollo_b200 import examples
+    low, B, _ = build_case(examples.cart_pole_swing_up(), "lobatto", K_SECTIONS, N_K,
+                           seed=0, unit_scaling=True)
+    rng = np.random.default_rng(os.getpid())
+    x = rng.uniform(-0.5, 0.5, low.S.num_x)
+    lam = rng.standard_normal(low.S.num_c)
+    B.G_nonzeros(x)
+    B.H_nonzeros(x, 1.0, lam)
+    q.put(("ready", os.getpid()))
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        B.G_nonzeros(x)
+        B.H_nonzeros(x, 1.0, lam)
+        n += 1
+    q.put(("done", n, time.perf_counter() - t0))
+
+
+def cpu_oracle_rate_all_cores(seconds=8.0, max_procs=16):
+    """Aggregate evals/s of `cores` independent evaluation streams, one process per
+    host core (the port is single-threaded, as the reference's evaluation is; this
+    is the multi-start throughput a host could reach with the same algorithm)."""
+    import multiprocessing as mp
+    cores = max(1, min(max_procs, os.cpu_count() or 1))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cpu_worker, args=(seconds, q)) for _ in range(cores)]
+    for p in procs:
+        p.start()
+    total, longest, done = 0, 0.0, 0
+    deadline = time.perf_counter() + 120.0 + seconds
+    while done < cores:
+        try:
+            msg = q.get(timeout=5)
+        except Exception:
+            if time.perf_counter() > deadline or not any(p.is_alive() for p in procs):
+                for p in procs:
+                    if p.is_alive():
+                        p.terminate()
+                raise RuntimeError("all-cores CPU leg: workers did not report")
+            continue
+        if msg[0] == "done":
+            total += msg[1]
+            longest = max(longest, msg[2])
+            done += 1
+    for p in procs:
+        p.join(timeout=30)
+    return {"value": total / longest, "unit": UNIT, "cores": cores,
+            "how": f"{cores} processes, one independent evaluation stream each, "
+                   f"{total} evaluations in {longest:.1f} s (windows overlap after a "
+                   f"staggered start: an upper bound of the sustained rate)"}
 
 
 def run_reference(args):
@@ -320,6 +381,10 @@ def run_cuda(args):
                    "sample": f"{n} fused G+H evaluations of the full 10^5-node "
                              f"workload in {dt:.1f} s by oracle/blockwise.py "
                              f"(numpy, 1 thread)"}
+            try:
+                cpu["all_cores"] = cpu_oracle_rate_all_cores()
+            except Exception as exc:                      # never fail the bench for this leg
+                cpu["all_cores"] = {"error": repr(exc)[:200]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
