@@ -263,6 +263,10 @@ def run_reference(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    try:
+        line["cpu_baseline"]["all_cores"] = cpu_oracle_rate_all_cores()
+    except Exception as exc:
+        line["cpu_baseline"]["all_cores"] = {"error": repr(exc)[:200]}
     print(json.dumps(line))
     return 0
 
