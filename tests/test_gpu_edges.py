@@ -165,3 +165,50 @@ def test_cyipopt_adapter_orderings_and_staging():
     assert np.all(np.diff(rows) >= 0)                              # row-major
     hr, hc = cb.hessianstructure()
     assert np.all(hr >= hc)                                        # lower triangle
+
+
+@pytest.mark.parametrize("name,K,nodes,kw", [
+    ("cart_pole_swing_up", 700, 4, {}),
+    ("double_pendulum", 6, [4, 7, 2, 10, 3, 5], dict(max_tile_nodes=20)),
+    ("multiphase_sliding_mass", 60, [3, 5, 4] * 20, dict(max_tile_nodes=24)),
+    ("delta_iii_launch_vehicle", 30, 4, {}),
+])
+def test_no_write_outside_the_output_arrays(name, K, nodes, kw):
+    """Guard bands around every input and output (compute-sanitizer is not available
+    on this pool): one arena, 512-double sentinels between the arrays, every
+    callback evaluated, every sentinel and every input intact afterwards."""
+    import torch
+    low, _, scal = build_case(getattr(examples, name)(), "lobatto", K, nodes, oracle=False, **kw)
+    S = low.S
+    eng = make_engine(low, scal)
+    sizes = dict(x=S.num_x, lam=S.num_c, sigma=1, f=1, grad=S.num_x, c=S.num_c, dy=S.num_dy,
+                 jac=S.nnz_g, hess=S.nnz_h)
+    G = 512
+    total = sum(sizes.values()) + G * (len(sizes) + 1)
+    SENT = -7.25e77
+    arena = torch.full((total,), SENT, dtype=torch.float64, device="cuda")
+    views, off = {}, G
+    for k, n in sizes.items():
+        views[k] = arena[off:off + n]
+        off += n + G
+    rng = np.random.default_rng(9)
+    lo, hi = (0.3, 0.45) if name == "delta_iii_launch_vehicle" else (-0.5, 0.5)
+    views["x"].copy_(torch.from_numpy(rng.uniform(lo, hi, S.num_x)))
+    views["lam"].copy_(torch.from_numpy(rng.standard_normal(S.num_c)))
+    views["sigma"].fill_(0.8)
+    x0, l0 = views["x"].clone(), views["lam"].clone()
+    what = E.EVAL_C | E.EVAL_DY | E.EVAL_JAC | E.EVAL_HESS | E.EVAL_F | E.EVAL_GRAD
+    for w in (what, E.EVAL_JAC | E.EVAL_HESS, E.EVAL_JAC, E.EVAL_HESS, E.EVAL_C | E.EVAL_DY):
+        eng.eval_ptr(w, views["x"], lam=views["lam"], sigma=views["sigma"],
+                     f=views["f"], grad=views["grad"], c=views["c"], dy=views["dy"],
+                     jac=views["jac"], hess=views["hess"])
+    torch.cuda.synchronize()
+    off = 0
+    for k, n in sizes.items():                     # guard band in front of every array
+        assert bool((arena[off:off + G] == SENT).all()), f"write in front of {k}"
+        off += G + n
+    assert bool((arena[off:off + G] == SENT).all()), "write behind the last array"
+    assert torch.equal(views["x"], x0) and torch.equal(views["lam"], l0)
+    for k in ("f", "grad", "c", "dy", "jac", "hess"):   # and every slot was written
+        assert not bool((views[k] == SENT).any()), f"unwritten slot in {k}"
+        assert bool(torch.isfinite(views[k]).all()), k
