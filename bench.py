@@ -7,27 +7,37 @@ num_c = 399 997, nnz_G = 3 899 963, nnz_H = 500 000), full-Hessian callbacks.
 One *step* = one evaluation of (G values, H values) for one synthetic iterate
 (x_tilde ~ U(-0.5, 0.5), lam ~ N(0, 1), sigma = 1) = ONE fused kernel launch.
 
-* ``value``  : device-resident inputs/outputs, CUDA events on the launch stream.
-  A ring of buffer sets larger than L2 is cycled so no step finds its inputs or
-  last outputs in L2.
+* ``value``  : device-resident inputs/outputs.  The K timed launches are issued by
+  ONE foreign call (``pcx_eval_many``): the stream is gated until all K are
+  enqueued and the bracketing CUDA events are recorded on the launch stream inside
+  that call, so the number does not depend on how fast Python enqueues.  A ring of
+  buffer sets larger than L2 is cycled so no step finds its inputs or last outputs
+  in L2.
+* ``latency_us``: one evaluation at a time, synchronised before and after, cold
+  ring slot -- what a strictly sequential host (one IPOPT) sees per callback.
 * ``e2e``    : same evaluation through the C-ABI call with HOST (pinned) buffers;
   H2D of x/lam/sigma and D2H of the values are inside the timed region.
 * ``roofline``: algorithmic bytes 8*(num_x+nnz_G) + 8*(num_x+num_c+nnz_H)
    per launch / mean launch time, against the measured copy
   bandwidth of MEASURED_PEAKS.json.
-* ``cpu_baseline``: the oracle port (``oracle/blockwise.py``, numpy, 1 thread)
-  on a bounded sample of the same workload.  One thread is the reference's own
-  degree of parallelism: its callbacks are CasADi SX virtual-machine evaluations,
-  single-threaded by construction ("where time goes").
-  ``cpu_baseline.all_cores`` adds, for transparency, the aggregate rate of one such
-  single-threaded evaluation stream per host core (independent iterates).
-* ``amortised``: informational -- the same kernel with 8 iterates per launch.
+* ``cpu_baseline``: the oracle port (``oracle/blockwise.py``, numpy, 1 thread) on a
+  bounded sample of the same workload -- one thread is the reference's own degree
+  of parallelism (CasADi SX virtual machine driven by one IPOPT).  Beside it:
+  ``numba`` (same port, node functions in one ``numba.prange`` kernel over all host
+  cores) and ``all_cores`` (one single-threaded stream per
+  core on independent iterates).
+* ``strong`` (N > 1 only): BASELINE config 4 -- ONE Delta III mesh (4 phases,
+  ~10^6 nodes) split over the N ranks by tile ranges, border values exchanged
+  inside the kernel over NVLink peer memory; checked in-process against the
+  unsharded evaluation, timed as max over ranks.
 * ``--impl reference``: the reference's CPU implementation of this path.  The
   live reference (CasADi) cannot be installed here (no casadi/pyproprop wheel,
-  no network), so this arm times the oracle port.
+  no network), so this arm times the oracle port with every host
+  thread it can use (numba node kernel) and reports the 1-thread figure beside it.
 
-Multi-GPU (``torchrun``): weak scaling, one independent multi-start instance of
-the same workload per rank, no data-path collective; time = max over ranks.
+Multi-GPU (``torchrun``): the headline is weak scaling, one independent
+multi-start instance of the same workload per rank, no data-path collective;
+time = max over ranks.
 """
 from __future__ import annotations
 
@@ -42,13 +52,13 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "tests")):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 METRIC = "Jacobian+Hessian callback evals/s at 10^5 mesh nodes"
 UNIT = "evals/s"
 K_SECTIONS, N_K = 33333, 4
+STRONG_K = 83333                       # x 3 new nodes x 4 phases = 10^6 nodes (config 4)
 
 
 def workload_config(n_gpus):
@@ -58,10 +68,11 @@ def workload_config(n_gpus):
             "inputs": "x~U(-0.5,0.5), lam~N(0,1), sigma=1, numpy default_rng(seed)",
             "l2_policy": "ring of 6 device buffer sets (255 MB > 126 MB L2), "
                          "one set per step",
-            "launch": "one fused kernel per evaluation, back to back on one stream with "
-                      "programmatic dependent launch (the next kernel's table-only prologue "
-                      "overlaps the previous kernel's drain; it waits for that kernel's "
-                      "completion before touching x, lam or any output)",
+            "launch": "one fused kernel per evaluation; the K timed launches are enqueued "
+                      "by one C call (pcx_eval_many) behind a stream gate, back to back on "
+                      "one stream with programmatic dependent launch (the next kernel's "
+                      "table-only prologue overlaps the previous kernel's drain; it waits "
+                      "for that kernel's completion before touching x, lam or any output)",
             "parallelism": f"{n_gpus} independent instance(s), one per GPU"}
 
 
@@ -119,17 +130,30 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_oracle_rate(seconds_budget=12.0, max_evals=200):
+# ------------------------------------------------------------------ CPU legs --
+def _oracle_port(node_eval="numpy"):
+    """The CPU restatement of the reference's algorithm on the bench workload
+    (the one place besides tests/ and smoke() that may execute oracle/)."""
+    from examples import problems
+    from examples.cases import lower_case
+    from oracle.blockwise import BlockwiseNLP
+    ocp = problems.cart_pole_swing_up()
+    low, meshes, scal = lower_case(ocp, "lobatto", K_SECTIONS, N_K, seed=0, unit_scaling=True)
+    B = BlockwiseNLP(ocp, low.ir.full_bounds,
+                     [dict(N=m.N, sI=m.sI_matrix, sA=m.sA_matrix, W=m.W_matrix) for m in meshes],
+                     W_ocp=scal[2], w=scal[3], prune=low.S.prune,
+                     scaling_method=ocp.settings.scaling_method, node_eval=node_eval)
+    return low, B
+
+
+def cpu_oracle_rate(node_eval="numpy", seconds_budget=10.0, max_evals=200):
     """Time the oracle port on the same workload; returns (evals/s, n, seconds)."""
-    from helpers import build_case
-    from pycollo_b200 import examples
-    low, B, _ = build_case(examples.cart_pole_swing_up(), "lobatto", K_SECTIONS, N_K,
-                           seed=0, unit_scaling=True)
+    low, B = _oracle_port(node_eval)
     rng = np.random.default_rng(0)
     x = rng.uniform(-0.5, 0.5, low.S.num_x)
     lam = rng.standard_normal(low.S.num_c)
     B.G_nonzeros(x)
-    B.H_nonzeros(x, 1.0, lam)                       # warm-up: builds merge plans
+    B.H_nonzeros(x, 1.0, lam)                       # warm-up: merge plans, numba compile
     n, t0 = 0, time.perf_counter()
     while n < max_evals and (time.perf_counter() - t0) < seconds_budget:
         B.G_nonzeros(x)
@@ -139,46 +163,13 @@ def cpu_oracle_rate(seconds_budget=12.0, max_evals=200):
     return n / dt, n, dt
 
 
-def batched_rate(low, scal, E, torch, dev, stream, alg_bytes, peak, batch=8, steps=20):
-    """Same kernel, `batch` independent iterates per launch (multi-start sweep,
-    grid.y = batch): what the fixed per-launch costs amortise to.  Informational;
-    the headline `value` stays one evaluation per launch."""
-    S = low.S
-    eng = E.Engine(S, low.layouts, low.header, batch=batch, device=dev.index)
-    eng.set_scaling(*scal)
-    what = E.EVAL_JAC | E.EVAL_HESS
-    g = torch.Generator(device=dev).manual_seed(7)
-    R = 2                                             # 2 x 8 x 46 MB > L2
-    xs = [torch.rand(batch, S.num_x, dtype=torch.float64, device=dev, generator=g) - 0.5 for _ in range(R)]
-    ls = [torch.randn(batch, S.num_c, dtype=torch.float64, device=dev, generator=g) for _ in range(R)]
-    js = [torch.empty(batch, S.nnz_g, dtype=torch.float64, device=dev) for _ in range(R)]
-    hs = [torch.empty(batch, S.nnz_h, dtype=torch.float64, device=dev) for _ in range(R)]
-    for i in range(3):
-        eng.eval_ptr(what, xs[i % R], lam=ls[i % R], jac=js[i % R], hess=hs[i % R], stream=stream)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        eng.eval_ptr(what, xs[i % R], lam=ls[i % R], jac=js[i % R], hess=hs[i % R], stream=stream)
-    e1.record()
-    torch.cuda.synchronize()
-    us = 1e3 * e0.elapsed_time(e1) / steps / batch
-    gbs = alg_bytes / us / 1e3
-    return {"batch_per_launch": batch, "us_per_eval": us, "evals_per_s": 1e6 / us,
-            "achieved_GBs": gbs, "frac": gbs / peak,
-            "note": "same kernel, 8 independent iterates per launch (grid.y); informational"}
-
-
 def _cpu_worker(seconds, q):
     """One process of the all-cores CPU throughput leg: the oracle port on the same
     workload, evaluations counted over a fixed wall-clock window."""
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     os.environ.setdefault("MKL_NUM_THREADS", "1")
-    from helpers import build_case
-    from pycollo_b200 import examples
-    low, B, _ = build_case(examples.cart_pole_swing_up(), "lobatto", K_SECTIONS, N_K,
-                           seed=0, unit_scaling=True)
+    low, B = _oracle_port("numpy")
     rng = np.random.default_rng(os.getpid())
     x = rng.uniform(-0.5, 0.5, low.S.num_x)
     lam = rng.standard_normal(low.S.num_c)
@@ -228,22 +219,47 @@ def cpu_oracle_rate_all_cores(seconds=8.0, max_procs=16):
                    f"staggered start: an upper bound of the sustained rate)"}
 
 
+def cpu_baseline_block(single_budget=10.0):
+    """The three CPU figures reported beside the GPU number."""
+    rate, n, dt = cpu_oracle_rate("numpy", single_budget)
+    cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"{n} fused G+H evaluations of the full 10^5-node workload in "
+                     f"{dt:.1f} s by oracle/blockwise.py (numpy, 1 thread)"}
+    try:
+        import numba
+        r2, n2, dt2 = cpu_oracle_rate("numba", single_budget)
+        cpu["numba"] = {"value": r2, "unit": UNIT, "cores": int(numba.get_num_threads()),
+                        "how": f"same port, node functions in one numba.njit(parallel=True) "
+                               f"prange kernel over the mesh nodes; {n2} evaluations in "
+                               f"{dt2:.1f} s (sparse assembly stays single-threaded numpy)"}
+    except Exception as exc:                          # never fail the bench for this leg
+        cpu["numba"] = {"error": repr(exc)[:200]}
+    try:
+        cpu["all_cores"] = cpu_oracle_rate_all_cores()
+    except Exception as exc:
+        cpu["all_cores"] = {"error": repr(exc)[:200]}
+    return cpu
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     steps, warmup = args.steps, args.warmup
-    from helpers import build_case
-    from pycollo_b200 import examples
-    low, B, _ = build_case(examples.cart_pole_swing_up(), "lobatto", K_SECTIONS, N_K,
-                           seed=0, unit_scaling=True)
+    kind_eval, cores = "numpy", 1
+    try:
+        import numba
+        kind_eval, cores = "numba", int(numba.get_num_threads())
+    except Exception:
+        pass
+    low, B = _oracle_port(kind_eval)
     rng = np.random.default_rng(0)
     xs = [rng.uniform(-0.5, 0.5, low.S.num_x) for _ in range(2)]
     lams = [rng.standard_normal(low.S.num_c) for _ in range(2)]
     for i in range(max(1, min(warmup, 3))):
         B.G_nonzeros(xs[i % 2])
         B.H_nonzeros(xs[i % 2], 1.0, lams[i % 2])
-    steps = max(1, min(steps, 60))                  # bounded: ~0.25 s per eval
+    steps = max(1, min(steps, 60))                  # bounded: ~0.1-0.25 s per eval
     t0 = time.perf_counter()
     for i in range(steps):
         B.G_nonzeros(xs[i % 2])
@@ -255,15 +271,19 @@ def run_reference(args):
             "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{steps} fused G+H evaluations of the full "
-                                       f"10^5-node workload by oracle/blockwise.py "
-                                       f"(numpy, 1 thread); the live reference "
-                                       f"(CasADi) is not installable here"},
+                                       f"10^5-node workload by oracle/blockwise.py, node "
+                                       f"functions evaluated by {kind_eval} on {cores} "
+                                       f"thread(s); the live reference (CasADi) is not "
+                                       f"installable here"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     try:
+        r1, n1, dt1 = cpu_oracle_rate("numpy", 8.0)
+        line["cpu_baseline"]["single_thread"] = {"value": r1, "unit": UNIT, "cores": 1,
+                                                 "sample": f"{n1} evaluations in {dt1:.1f} s"}
         line["cpu_baseline"]["all_cores"] = cpu_oracle_rate_all_cores()
     except Exception as exc:
         line["cpu_baseline"]["all_cores"] = {"error": repr(exc)[:200]}
@@ -271,12 +291,116 @@ def run_reference(args):
     return 0
 
 
+# ------------------------------------------------------------------ GPU legs --
+def batched_rate(low, scal, E, torch, dev, stream, alg_bytes, peak, batch=8, steps=20):
+    """Same kernel, `batch` independent iterates per launch (multi-start sweep,
+    grid.y = batch): what the fixed per-launch costs amortise to.  Informational;
+    the headline `value` stays one evaluation per launch."""
+    S = low.S
+    eng = E.Engine(S, low.layouts, low.header, batch=batch, device=dev.index)
+    eng.set_scaling(*scal)
+    what = E.EVAL_JAC | E.EVAL_HESS
+    g = torch.Generator(device=dev).manual_seed(7)
+    R = 2                                             # 2 x 8 x 46 MB > L2
+    sets = [dict(x=torch.rand(batch, S.num_x, dtype=torch.float64, device=dev, generator=g) - 0.5,
+                 lam=torch.randn(batch, S.num_c, dtype=torch.float64, device=dev, generator=g),
+                 jac=torch.empty(batch, S.nnz_g, dtype=torch.float64, device=dev),
+                 hess=torch.empty(batch, S.nnz_h, dtype=torch.float64, device=dev))
+            for _ in range(R)]
+    args = eng.make_args(sets)
+    eng.eval_many(what, args, 3, stream=stream, gate=False, timed=False)
+    torch.cuda.synchronize()
+    ms = eng.eval_many(what, args, steps, stream=stream, gate=True, timed=True)
+    us = 1e3 * ms / steps / batch
+    gbs = alg_bytes / us / 1e3
+    return {"batch_per_launch": batch, "us_per_eval": us, "evals_per_s": 1e6 / us,
+            "achieved_GBs": gbs, "frac": gbs / peak,
+            "note": "same kernel, 8 independent iterates per launch (grid.y); informational"}
+
+
+def strong_scaling(args, torch, dist, E, rank, world, local_rank):
+    """BASELINE config 4 under the driver's own launch: ONE Delta III mesh (4 phases,
+    ~10^6 nodes) split over the ranks by tile ranges, border values exchanged inside
+    the kernel over NVLink peer memory (no NCCL call on the data path).  Asserts
+    parity with the unsharded evaluation (each value slot has exactly one writer:
+    the sum over ranks of the zero-initialised arrays must equal it) and times
+    unsharded (every rank runs it; max over ranks) and sharded, max over ranks."""
+    from examples import problems
+    from examples.cases import lower_case
+    from pycollo_b200.parallel import MeshSharder
+    K = args.strong_sections
+    dev = torch.device("cuda", local_rank)
+    what = E.EVAL_JAC | E.EVAL_HESS
+    ocp = problems.delta_iii_launch_vehicle()
+    # the tiling is built for world x 148 SMs, so a rank's share of the tiles is a
+    # whole number of waves of ITS 148 SMs
+    low, _, scal = lower_case(ocp, "lobatto", K, 4, seed=0, sm_count=148 * world)
+    S = low.S
+    eng = E.Engine(S, low.layouts, low.header, device=local_rank, structure=False)
+    eng.set_scaling(*scal)
+    g = torch.Generator(device=dev).manual_seed(0)              # same x / lam on every rank
+    x = 0.1 + 0.3 * torch.rand(S.num_x, dtype=torch.float64, device=dev, generator=g)
+    lam = torch.randn(S.num_c, dtype=torch.float64, device=dev, generator=g)
+    R = 2
+    jac = [torch.zeros(S.nnz_g, dtype=torch.float64, device=dev) for _ in range(R)]
+    hes = [torch.zeros(S.nnz_h, dtype=torch.float64, device=dev) for _ in range(R)]
+    st = torch.cuda.current_stream().cuda_stream
+    steps = max(5, min(args.steps, 30))
+    sets = [dict(x=x, lam=lam, jac=jac[k], hess=hes[k]) for k in range(R)]
+    cargs = eng.make_args(sets)
+    # ---- unsharded on this rank (the N = 1 time of the same engine) ------------
+    eng.eval_many(what, cargs, 3, stream=st, gate=False, timed=False)
+    torch.cuda.synchronize()
+    ms1 = eng.eval_many(what, cargs, steps, stream=st, gate=True, timed=True) / steps
+    ref_j, ref_h = jac[(steps - 1) % R].clone(), hes[(steps - 1) % R].clone()
+    # ---- sharded, fused exchange ----------------------------------------------------
+    sh = MeshSharder(eng, world, rank, border_rank=0, fused=True)
+    jac[0].zero_()
+    hes[0].zero_()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sh.evaluate(what, x, lam=lam, jac=jac[0], hess=hes[0])
+    dist.all_reduce(jac[0])
+    dist.all_reduce(hes[0])                                     # check only: sum of disjoint slabs
+    torch.cuda.synchronize()
+    ej = float((jac[0] - ref_j).abs().max() / ref_j.abs().max())
+    eh = float((hes[0] - ref_h).abs().max() / ref_h.abs().max())
+    assert ej <= 1e-13 and eh <= 1e-13, f"sharded != unsharded: jac {ej:.2e} hess {eh:.2e}"
+    for i in range(3):
+        sh.evaluate(what, x, lam=lam, jac=jac[i % R], hess=hes[i % R])
+    torch.cuda.synchronize()
+    dist.barrier()
+    msN = eng.eval_many(what, cargs, steps, stream=st, gate=True, timed=True) / steps
+    assert eng.status() == 0, "fused exchange timed out"
+    t = torch.tensor([ms1, msN], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms1, msN = float(t[0]), float(t[1])
+    alg = 8 * (S.num_x + S.nnz_g) + 8 * (S.num_x + S.num_c + S.nnz_h)
+    lo, hi = sh.lo, sh.hi
+    del jac, hes, ref_j, ref_h
+    torch.cuda.empty_cache()
+    return {"workload": "delta_iii_launch_vehicle, 4 phases x %d sections x 4 nodes = %d "
+                        "collocation nodes, ONE mesh over %d GPUs (tile ranges)"
+                        % (K, int(sum(t_.N for t_ in S.ph)), world),
+            "num_x": int(S.num_x), "nnz_G": int(S.nnz_g), "nnz_H": int(S.nnz_h),
+            "tiles": int(S.num_tiles), "tiles_rank0": int(hi - lo),
+            "scaling": "strong", "ms_per_eval_1gpu": ms1, "ms_per_eval": msN,
+            "speedup_vs_1gpu": ms1 / msN, "evals_per_s": 1e3 / msN,
+            "algorithmic_GBs": alg / msN / 1e6,
+            "comm": "fused in-kernel exchange over NVLink peer memory (CUDA IPC mapping of "
+                    "the border rank's buffer; st.release.sys / ld.acquire.sys epoch flags, "
+                    "double-buffered shares); no NCCL call on the data path",
+            "nvlink_bytes_per_eval": int(8 * (S.bv_size + 1) * (world - 1)),
+            "parity": {"vs": "unsharded evaluation on the same engine", "rel_err_jac": ej,
+                       "rel_err_hess": eh}, "steps": steps}
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
-    from helpers import build_case, make_engine
+    from examples import problems
+    from examples.cases import lower_case
     from pycollo_b200 import engine as E
-    from pycollo_b200 import examples
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -286,10 +410,13 @@ def run_cuda(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    steps, warmup = args.steps, max(args.warmup, 3)
+    steps, warmup = args.steps, args.warmup
+    if warmup < 3:
+        print(f"bench.py: --warmup {warmup} raised to 3 (timing rule: W >= 3)", file=sys.stderr)
+        warmup = 3
 
-    low, _, scal = build_case(examples.cart_pole_swing_up(), "lobatto", K_SECTIONS, N_K,
-                              seed=0, unit_scaling=True, oracle=False)
+    low, _, scal = lower_case(problems.cart_pole_swing_up(), "lobatto", K_SECTIONS, N_K,
+                              seed=0, unit_scaling=True)
     S = low.S
     eng = E.Engine(S, low.layouts, low.header, batch=1, device=local_rank)
     eng.set_scaling(*scal)
@@ -300,42 +427,39 @@ def run_cuda(args):
     R = 6
     rng = np.random.default_rng(1000 + rank)
     dev = torch.device("cuda", local_rank)
-    xs = [torch.from_numpy(rng.uniform(-0.5, 0.5, S.num_x)).to(dev) for _ in range(R)]
-    lams = [torch.from_numpy(rng.standard_normal(S.num_c)).to(dev) for _ in range(R)]
-    jacs = [torch.empty(S.nnz_g, dtype=torch.float64, device=dev) for _ in range(R)]
-    hess = [torch.empty(S.nnz_h, dtype=torch.float64, device=dev) for _ in range(R)]
+    sets = [dict(x=torch.from_numpy(rng.uniform(-0.5, 0.5, S.num_x)).to(dev),
+                 lam=torch.from_numpy(rng.standard_normal(S.num_c)).to(dev),
+                 jac=torch.empty(S.nnz_g, dtype=torch.float64, device=dev),
+                 hess=torch.empty(S.nnz_h, dtype=torch.float64, device=dev)) for _ in range(R)]
     stream = torch.cuda.current_stream().cuda_stream
-
-    # one pre-bound C-ABI call per ring slot: pcx_eval with its arguments converted
-    # once, as a compiled host would hold them
-    calls = [eng.bind(what, xs[k], lam=lams[k], jac=jacs[k], hess=hess[k], stream=stream)
-             for k in range(R)]
-
-    def step(i):
-        calls[i % R]()
+    cargs = eng.make_args(sets)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(warmup):
-        step(i)
+    eng.eval_many(what, cargs, warmup, stream=stream, gate=False, timed=False)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
     l0 = eng.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev0.record()
-    for i in range(steps):
-        step(i)
-    ev1.record()
+    ms = eng.eval_many(what, cargs, steps, stream=stream, gate=True, timed=True)
     barrier()
-    ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count - l0
+
+    # ---- single-evaluation latency (sequential host) --------------------------
+    lat = []
+    one = [eng.make_args([s]) for s in sets]
+    for i in range(3 + 24):
+        torch.cuda.synchronize()
+        t_ms = eng.eval_many(what, one[i % R], 1, stream=stream, gate=False, timed=True)
+        if i >= 3:
+            lat.append(1e3 * t_ms)
+    launches += 27
 
     # ---- end to end through the C ABI with pinned host buffers ------------
     hx = torch.from_numpy(rng.uniform(-0.5, 0.5, S.num_x)).pin_memory()
@@ -344,24 +468,33 @@ def run_cuda(args):
     hj = torch.empty(S.nnz_g, dtype=torch.float64).pin_memory()
     hh = torch.empty(S.nnz_h, dtype=torch.float64).pin_memory()
     e2e_steps = max(3, min(steps, 50))
+    call = eng.bind(what, hx, lam=hl, sigma=hs, jac=hj, hess=hh, space=E.PCX_HOST, stream=stream)
     for _ in range(3):
-        eng.eval_ptr(what, hx, lam=hl, sigma=hs, jac=hj, hess=hh, space=E.PCX_HOST,
-                     stream=stream)
+        call()
     barrier()
     l1 = eng.launch_count
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        eng.eval_ptr(what, hx, lam=hl, sigma=hs, jac=hj, hess=hh, space=E.PCX_HOST,
-                     stream=stream)
+        call()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     launches += eng.launch_count - l1
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([ms, 1e3 * e2e_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, 1e3 * e2e_s, float(np.median(lat))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    ms_max, e2e_ms_max, lat_us = float(t[0]), float(t[1]), float(t[2])
+
+    strong = None
+    if world > 1 and not args.no_strong:
+        del sets, cargs, one, hj, hh
+        torch.cuda.empty_cache()
+        try:
+            strong = strong_scaling(args, torch, dist, E, rank, world, local_rank)
+        except Exception as exc:                      # reported, never hides the headline
+            strong = {"error": repr(exc)[:300]}
+
     if rank == 0:
         value = world * steps / (ms_max * 1e-3)
         e2e_value = world * e2e_steps / (e2e_ms_max * 1e-3)
@@ -376,19 +509,11 @@ def run_cuda(args):
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         amortised = None
+        cpu = None
         if world == 1:
             amortised = batched_rate(low, scal, E, torch, dev, stream, alg_bytes, peak)
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            rate, n, dt = cpu_oracle_rate()
-            cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"{n} fused G+H evaluations of the full 10^5-node "
-                             f"workload in {dt:.1f} s by oracle/blockwise.py "
-                             f"(numpy, 1 thread)"}
-            try:
-                cpu["all_cores"] = cpu_oracle_rate_all_cores()
-            except Exception as exc:                      # never fail the bench for this leg
-                cpu["all_cores"] = {"error": repr(exc)[:200]}
+            if not args.no_cpu_baseline:
+                cpu = cpu_baseline_block()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -398,6 +523,9 @@ def run_cuda(args):
                              "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes,
                              "kernel": "pcx_fill_12 (fused Jacobian+Hessian fill)"},
+                "latency_us": {"value": lat_us, "frac": alg_bytes / lat_us / 1e3 / peak,
+                               "how": "one evaluation per synchronised call, cold ring slot, "
+                                      "CUDA events around the single launch; median of 24"},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT,
                         "h2d_bytes_per_step": 8 * (S.num_x + S.num_c + 1),
@@ -406,6 +534,8 @@ def run_cuda(args):
                                                    "host buffers"},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "amortised": amortised}
+        if strong is not None:
+            line["strong"] = strong
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -419,6 +549,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true",
+                    help="skip the mesh-sharded (config 4) leg of a multi-GPU run")
+    ap.add_argument("--strong-sections", type=int, default=STRONG_K,
+                    help="sections per phase of the sharded Delta III mesh")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -1,7 +1,12 @@
-"""Problem definitions used by the tests, ``bench.py`` and ``smoke()``.
+"""User scripts: the optimal control problems the tests, ``bench.py``, ``smoke()``
+and the golden-vector generator evaluate.
 
 Each builder returns a fully defined, un-initialised ``OptimalControlProblem``
-written exactly as a pycollo user would write it.  The problem data
+written exactly as a pycollo user writes it -- so exactly that the same function
+builds the problem on EITHER package: ``api=None`` (default) uses
+``pycollo_b200``; ``oracle/make_golden_nlp.py`` passes the reference's own
+``pycollo`` module (imported from ``/root/reference`` in the build container) to
+produce the golden vectors the CUDA path is checked against.  The problem data
 (equations, bounds, guesses) are those of the reference's example scripts and
 unit-test fixtures, cited per function; they are *inputs* to the engine.
 
@@ -12,25 +17,36 @@ from __future__ import annotations
 import numpy as np
 import sympy as sym
 
-from .mesh import PhaseMesh
-from .problem import OptimalControlProblem
+
+def _ocp_class(api):
+    if api is None:
+        import pycollo_b200 as api
+    return api.OptimalControlProblem
 
 
 def set_mesh(problem, number_mesh_sections, number_mesh_section_nodes=4,
              mesh_section_sizes=None, phases=None):
-    """Give (selected) phases a mesh of K sections x N_k nodes."""
+    """Give (selected) phases a mesh of K sections x N_k nodes (either package:
+    the three user-facing attributes of ``pycollo/mesh.py:10-121``)."""
     for ph in (problem.phases if phases is None else phases):
-        ph.mesh = PhaseMesh(number_mesh_sections, mesh_section_sizes,
-                            number_mesh_section_nodes)
+        m = ph.mesh
+        if hasattr(type(m), "number_mesh_sections"):      # reference: validated setters
+            m._mesh_sec_sizes = None
+            m.number_mesh_sections = number_mesh_sections
+            m.mesh_section_sizes = mesh_section_sizes
+            m.number_mesh_section_nodes = number_mesh_section_nodes
+        else:
+            ph.mesh = type(m)(number_mesh_sections, mesh_section_sizes,
+                              number_mesh_section_nodes)
     return problem
 
 
-def brachistochrone(quadrature_method="lobatto", scaling_method="bounds"):
+def brachistochrone(quadrature_method="lobatto", scaling_method="bounds", api=None):
     """``examples/brachistochrone/brachistochrone.py``,
     ``tests/unit/conftest.py:14-76`` (n_y=3, n_u=1, n_t=1)."""
     x, y, v, u = sym.symbols("x y v u")
     g = 9.81
-    problem = OptimalControlProblem(name="Brachistochrone")
+    problem = _ocp_class(api)(name="Brachistochrone")
     phase = problem.new_phase(name="A")
     phase.state_variables = [x, y, v]
     phase.control_variables = u
@@ -52,7 +68,7 @@ def brachistochrone(quadrature_method="lobatto", scaling_method="bounds"):
     return problem
 
 
-def double_pendulum():
+def double_pendulum(api=None):
     """``tests/unit/conftest.py:79-190`` (aux-data heavy; n_y=4, n_u=2, n_q=1,
     n_t=1, n_s=2; phase-level aux data shadow problem-level ones)."""
     a0, a1, v0, v1, T0, T1 = sym.symbols("a0 a1 v0 v1 T0 T1")
@@ -66,7 +82,7 @@ def double_pendulum():
               + m1 * p1 * l0 * (s1 * c0 - s0 * c1) * v1 ** 2)
     K1_eqn = (T1 + g * m1 * p1 * c1
               + m1 * p1 * l0 * (s0 * c1 - s1 * c0) * v0 ** 2)
-    problem = OptimalControlProblem(name="Double Pendulum Swing-Up")
+    problem = _ocp_class(api)(name="Double Pendulum Swing-Up")
     phase = problem.new_phase(name="A")
     phase.state_variables = [a0, a1, v0, v1]
     phase.control_variables = [T0, T1]
@@ -108,11 +124,11 @@ def double_pendulum():
     return problem
 
 
-def hypersensitive(quadrature_method="lobatto"):
+def hypersensitive(quadrature_method="lobatto", api=None):
     """``examples/hypersensitive_problem/hypersensitive_problem.py``
     (n_y = n_u = n_q = 1, fixed times)."""
     y, u = sym.symbols("y u")
-    problem = OptimalControlProblem(name="Hypersensitive problem")
+    problem = _ocp_class(api)(name="Hypersensitive problem")
     phase = problem.new_phase(name="A")
     phase.state_variables = y
     phase.control_variables = u
@@ -135,13 +151,13 @@ def hypersensitive(quadrature_method="lobatto"):
     return problem
 
 
-def cart_pole_swing_up(quadrature_method="lobatto", scaling_method="bounds"):
+def cart_pole_swing_up(quadrature_method="lobatto", scaling_method="bounds", api=None):
     """``examples/cart_pole_swing_up/cart_pole_swing_up_explicit.py``
     (n_y=4, n_u=1, n_q=1, n_t=0) -- the BASELINE.json config-2 problem."""
     q1, q2, q1d, q2d, q1dd, q2dd, F = sym.symbols("q1 q2 q1d q2d q1dd q2dd F")
     m1, m2, l, g = sym.symbols("m1 m2 l g")
     F_max, d_max, d, T = 20.0, 2.0, 1.0, 2.0
-    problem = OptimalControlProblem(name="Cart-Pole Swing-Up")
+    problem = _ocp_class(api)(name="Cart-Pole Swing-Up")
     phase = problem.new_phase(name="A")
     phase.state_variables = [q1, q2, q1d, q2d]
     phase.control_variables = F
@@ -173,13 +189,13 @@ def cart_pole_swing_up(quadrature_method="lobatto", scaling_method="bounds"):
     return problem
 
 
-def free_flying_robot(quadrature_method="lobatto"):
+def free_flying_robot(quadrature_method="lobatto", api=None):
     """``examples/free_flying_robot/free_flying_robot.py`` (n_y=6, n_u=4, n_p=2,
     n_q=1, fixed times) -- BASELINE config 3."""
     r_x, r_y, theta, v_x, v_y, omega = sym.symbols("r_x r_y theta v_x v_y omega")
     u_x_pos, u_x_neg, u_y_pos, u_y_neg = sym.symbols("u_x_pos u_x_neg u_y_pos u_y_neg")
     T_x, T_y, I_xx, I_yy = sym.symbols("T_x T_y I_xx I_yy")
-    problem = OptimalControlProblem(name="Free-Flying Robot")
+    problem = _ocp_class(api)(name="Free-Flying Robot")
     phase = problem.new_phase(name="A",
                               state_variables=[r_x, r_y, theta, v_x, v_y, omega],
                               control_variables=[u_x_pos, u_x_neg, u_y_pos, u_y_neg])
@@ -218,7 +234,7 @@ def free_flying_robot(quadrature_method="lobatto"):
     return problem
 
 
-def space_shuttle_reentry(quadrature_method="lobatto"):
+def space_shuttle_reentry(quadrature_method="lobatto", api=None):
     """``examples/space_shuttle_reentry_trajectory/...maximum_crossrange.py``
     (n_y=6, n_u=2, free final time) -- BASELINE config 3."""
     h, phi, theta, nu, gamma, psi, alpha, beta = sym.symbols(
@@ -227,7 +243,7 @@ def space_shuttle_reentry(quadrature_method="lobatto"):
         "D L g r rho rho_0 h_r c_L c_D Re S")
     c_lift_0, c_lift_1, mu, c_drag_0, c_drag_1, c_drag_2, m = sym.symbols(
         "c_lift_0 c_lift_1 mu c_drag_0 c_drag_1 c_drag_2 m")
-    problem = OptimalControlProblem(
+    problem = _ocp_class(api)(
         name="Space shuttle reentry trajectory maximum crossrange")
     phase = problem.new_phase(name="A")
     phase.state_variables = [h, phi, theta, nu, gamma, psi]
@@ -275,13 +291,13 @@ def space_shuttle_reentry(quadrature_method="lobatto"):
     return problem
 
 
-def multiphase_sliding_mass(num_phases=3):
+def multiphase_sliding_mass(num_phases=3, api=None):
     """``tests/integration/test_multiphase.py:25-75``: unit mass slid from 0 to 1,
     split in phases linked by endpoint constraints on velocity and time."""
     x, v, f = sym.symbols("x v f")
     MAX_T, MAX_V, MAX_F = 1.0, 10.0, 20.0
     names = {0: "A", 1: "B", 2: "C", 3: "D"}
-    problem = OptimalControlProblem(f"{num_phases}-phase Sliding Mass")
+    problem = _ocp_class(api)(f"{num_phases}-phase Sliding Mass")
     for i in range(num_phases):
         start_x, end_x = i / num_phases, (i + 1) / num_phases
         phase = problem.new_phase(names[i], state_variables=[x, v],
@@ -309,7 +325,7 @@ def multiphase_sliding_mass(num_phases=3):
     return problem
 
 
-def delta_iii_launch_vehicle():
+def delta_iii_launch_vehicle(api=None):
     """``examples/delta_iii_launch_vehicle/delta_iii_launch_vehicle.py``: 4 phases,
     n_y=7, n_u=3, n_p=2 each, 18 linkage constraints, phase-dependent auxiliary
     data (T, xi) -- BASELINE config 4.  The reference marks this example as not
@@ -338,7 +354,7 @@ def delta_iii_launch_vehicle():
     m_tF_C = m_t0_C - ((1 - (2 * (tau_burn_S / tau_burn_1))) * m_prop_1)
     m_t0_D = m_tF_C - m_struct_1
     m_tF_D = m_payload
-    problem = OptimalControlProblem(name="Delta III Launch Vehicle Ascent Problem")
+    problem = _ocp_class(api)(name="Delta III Launch Vehicle Ascent Problem")
     A_ = -mu / (r_vec_norm ** 3)
     v_y_t0 = omega_E * R_E * sym.cos(psi_L)
     masses = [(m_t0_A, m_tF_A), (m_t0_B, m_tF_B), (m_t0_C, m_tF_C), (m_t0_D, m_tF_D)]

@@ -153,12 +153,20 @@ int pcx_set_shard(pcx_engine* e, int tile_begin, int tile_end);
  * share of the border values straight into the border rank's memory over NVLink
  * (system-scope release), and the border rank's kernel waits for all shares,
  * sums them in rank order and writes the border slots itself.  All ranks must
- * call pcx_eval the same number of times (an epoch counter pairs the calls).   */
+ * call pcx_eval the same number of times (an epoch counter pairs the calls).
+ * No host-side synchronisation between evaluations is needed: the share slots
+ * are double-buffered by epoch parity and a rank reuses a slot only after the
+ * border rank has published that it consumed it, so a rank runs at most two
+ * evaluations ahead of the border rank.                                        */
 int pcx_exchange_alloc(pcx_engine* e, int world, unsigned char handle[64]);
 int pcx_exchange_attach(pcx_engine* e, int rank, int world, int border_rank,
                         const unsigned char handle[64]);
 int pcx_exchange_attach_ptr(pcx_engine* e, int rank, int world, int border_rank, void* base);
 int pcx_exchange_buffer(pcx_engine* e, void** base);
+/* Sticky device-side status word of the engine (synchronising copy): 0 = ok,
+ * 1 = a fused exchange gave up waiting for a peer rank (5 s) -- the values of
+ * that evaluation are not valid.                                              */
+int pcx_status(pcx_engine* e, int* code);
 int pcx_shard_buffer(pcx_engine* e, double** xbuf, int64_t* n);
 int pcx_apply_border(pcx_engine* e, int what, const double* x, const double* lam,
                      const double* sigma, double* f, double* grad, double* c,
@@ -206,12 +214,72 @@ int pcx_refit_size(const pcx_engine* e, int64_t* num_x_ph);
  * layout of a previous mesh with prev_N[p] nodes in phase p at abscissae
  * prev_tau (phases concatenated), tau the new mesh's abscissae (phases
  * concatenated, N_p each).  y and u rows are interpolated with interp1d's own
- * formula slope*(t - t_lo) + y_lo, lo/hi from a left bisection clipped to
+ * formula ((t - t_lo)/(t_hi - t_lo))*y_hi + ((t_hi - t)/(t_hi - t_lo))*y_lo (scipy >= 1.10), lo/hi from a left bisection clipped to
  * [1, M-1]; q, t and s are copied (iteration.py:166-168).  prev_N is a host
  * array of num_phases entries whatever `space` is.                            */
 int pcx_interp_guess(pcx_engine* e, const double* x_prev, const double* prev_tau,
                      const int64_t* prev_N, const double* tau, double* x_guess,
                      int space, void* stream);
+
+/* ---- sparsity structure for a C/C++ host ----------------------------------
+ * Replaces Casadi.evaluate_G_structure (pycollo/backend.py:1747-1761) and the
+ * cyipopt contract jacobianstructure() / hessianstructure()
+ * (pycollo/nlp.py:36-76).  The patterns are fixed per (problem, mesh); they are
+ * handed to pcx_create as the optional int64 tables "g_rows", "g_cols",
+ * "h_rows", "h_cols" (value order of pcx_eval) and kept on the host.
+ *   PCX_ORDER_NATIVE   : the order pcx_eval writes -- Jacobian in CCS order
+ *                        (by column, then row), Hessian upper triangle in CCS
+ *                        order (row <= col); perm = identity;
+ *   PCX_ORDER_ROW_MAJOR: Jacobian by row, then column; Hessian as the LOWER
+ *                        triangle by row, then column (the transposed upper
+ *                        triangle: same value order, rows/cols swapped).
+ * rows/cols/perm have nnz entries (pcx_sizes); perm may be NULL.  Values in the
+ * requested order are values_native[perm[i]] (pcx_gather does it on the device). */
+#define PCX_ORDER_NATIVE    0
+#define PCX_ORDER_ROW_MAJOR 1
+int pcx_structure_jac(const pcx_engine* e, int order, int64_t* rows, int64_t* cols,
+                      int64_t* perm);
+int pcx_structure_hess(const pcx_engine* e, int order, int64_t* rows, int64_t* cols,
+                       int64_t* perm);
+
+/* ---- iteration scaling from the sparse Jacobian --
+ * Replaces the dense np.array(G) + row norms of
+ * IterationScaling._calculate_constraint_scaling (pycollo/scaling.py:392-396):
+ * evaluates the Jacobian at x with the scaling currently set and writes
+ * norms[i] = sqrt(sum_j G[i,j]^2) for every constraint row (num_c doubles); the
+ * Jacobian values never leave the device.  Needs the structure tables.        */
+int pcx_jac_row_norms(pcx_engine* e, const double* x, double* norms, int space,
+                      void* stream);
+
+/* ---- variable / constraint bounds on the mesh ----
+ * Replaces Iteration.generate_variable_bounds / generate_constraint_bounds /
+ * scale_bounds (pycollo/iteration.py:408-453): OCP-level bounds (one (lo, hi)
+ * pair per OCP variable in the order [per phase: y, u, q, t] ++ [s]; per OCP
+ * constraint in the order [per phase: defect, path, integral] ++ [endpoint];
+ * state bounds at t0 / tF per phase state) are expanded to the mesh and scaled:
+ *   x_lo[i] = (1/V[i]) * (lo - r[i])   (scaling.py:172-174),  c_lo[i] = W[i] * lo.
+ * All inputs are HOST arrays (they are O(#OCP variables)); outputs follow
+ * `space`.  y_t0 / y_tF hold 2 doubles (lo, hi) per state, phases concatenated. */
+int pcx_expand_bounds(pcx_engine* e, const double* ocp_x_bnd, const double* y_t0_bnd,
+                      const double* y_tF_bnd, const double* ocp_c_bnd,
+                      const double* V_ocp, const double* r_ocp, const double* W_ocp,
+                      double* x_lo, double* x_hi, double* c_lo, double* c_hi,
+                      int space, void* stream);
+
+/* ---- many evaluations, one foreign call -------------------------------------
+ * `count` evaluations enqueued back to back on `stream` from C, cycling through
+ * `n_sets` argument sets (device pointers; a sweep over iterates, or a ring of
+ * buffers larger than L2).  With gate != 0 the stream is held by a one-thread
+ * kernel until every launch has been enqueued, so the device-side time does not
+ * depend on how fast the host enqueues.  If elapsed_ms is not NULL the call
+ * brackets the `count` launches with CUDA events on `stream` (after the gate),
+ * synchronises and returns the elapsed time.                                  */
+typedef struct {
+    const double *x, *lam, *sigma;
+    double *f, *grad, *c, *dy, *jac, *hess;
+} pcx_args;
+int pcx_eval_many(pcx_engine* e, int what, const pcx_args* sets, int n_sets,
+                  int count, void* stream, int gate, float* elapsed_ms);
 
 /* Sizes (per instance) -- Casadi.evaluate_G_num_nonzero backend.py:1763-1771 */
 int pcx_sizes(const pcx_engine* e, int64_t* num_x, int64_t* num_c, int64_t* num_dy,

@@ -50,6 +50,54 @@ class _Fn:
                           for o in out])
 
 
+class _FnNumba:
+    """Same contract as ``_Fn``, but the expressions are evaluated by ONE
+    ``numba.njit(parallel=True)`` kernel that loops over the mesh nodes with
+    ``prange`` -- the node-parallel CPU baseline of SURVEY.md section 8(d)(ii)
+    (the reference's dead stack planned exactly this: ``@nb.njit`` at
+    ``pycollo/numbafy.py:232``).  The scalar body is sympy's own code printer
+    output after ``cse``; threads = ``numba.get_num_threads()``."""
+
+    _count = 0
+
+    def __init__(self, args, exprs):
+        self.n = len(exprs)
+        self.kernel = None
+        if not exprs:
+            return
+        import math
+        import numba
+        from sympy.printing.pycode import pycode
+        args = list(args)
+        # user symbol names may shadow builtins or be invalid identifiers: rename
+        safe = [sym.Symbol(f"v{i}_") for i in range(len(args))]
+        exprs = [sym.sympify(e).xreplace(dict(zip(args, safe))) for e in exprs]
+        rep, red = sym.cse(exprs, symbols=sym.numbered_symbols("_t"))
+        lines = ["def _kernel(N, out, %s):" % ", ".join(f"c{i}" for i in range(len(args))),
+                 "    for m in prange(N):"]
+        lines += [f"        v{i}_ = c{i}[m]" for i in range(len(args))]
+        lines += [f"        {lhs} = {pycode(rhs, fully_qualified_modules=False)}" for lhs, rhs in rep]
+        lines += [f"        out[{k}, m] = {pycode(e, fully_qualified_modules=False)}"
+                  for k, e in enumerate(red)]
+        src = "\n".join(lines)
+        ns = {"prange": numba.prange, "math": math}
+        ns.update({k: getattr(math, k) for k in ("sin", "cos", "tan", "exp", "log", "sqrt",
+                                                  "asin", "acos", "atan", "atan2", "sinh",
+                                                  "cosh", "tanh", "pi", "fabs")})
+        exec(src, ns)
+        _FnNumba._count += 1
+        self.kernel = numba.njit(parallel=True, fastmath=False, cache=False)(ns["_kernel"])
+
+    def __call__(self, cols, N):
+        if not self.n:
+            return np.empty((0, N))
+        out = np.empty((self.n, N))
+        cols = [np.ascontiguousarray(np.broadcast_to(np.asarray(c, dtype=float), (N,)))
+                for c in cols]
+        self.kernel(N, out, *cols)
+        return out
+
+
 class _MergePlan:
     """Sort COO triplets column-major and sum duplicates (pattern fixed once)."""
 
@@ -73,7 +121,10 @@ class _MergePlan:
 
 class BlockwiseNLP:
     def __init__(self, ocp, bounds, meshes, *, scaling_method="bounds", w=1.0,
-                 W_ocp=None, prune=True):
+                 W_ocp=None, prune=True, node_eval="numpy"):
+        """``node_eval``: "numpy" (vectorised, one thread) or "numba" (one
+        ``prange`` kernel over the nodes, all host cores)."""
+        _Fn_ = _Fn if node_eval == "numpy" else _FnNumba
         lp = lower(ocp, bounds, scaling_method)
         self.lp = lp
         self.meshes = meshes
@@ -126,9 +177,9 @@ class BlockwiseNLP:
                             d2.append((e, a, b))
             rec = dict(
                 fns=fns, fam=fam, nv=len(v), d1=d1, d2=d2,
-                val=_Fn(allv, fns),
-                jac=_Fn(allv, [sym.diff(fns[e], allv[a]) for e, a in d1]),
-                hes=_Fn(allv, [sym.diff(fns[e], allv[a], allv[b])
+                val=_Fn_(allv, fns),
+                jac=_Fn_(allv, [sym.diff(fns[e], allv[a]) for e, a in d1]),
+                hes=_Fn_(allv, [sym.diff(fns[e], allv[a], allv[b])
                                for e, a, b in d2]),
                 nonzero_fn=[_nz(e) for e in fns],
             )

@@ -144,7 +144,7 @@ def dump_mesh_error(tag, method, problem, sizes, nodes, seed):
     ``dy_ph`` come from the oracle (the reference evaluates them with CasADi)."""
     sys.path.insert(0, os.path.dirname(HERE))
     from oracle.blockwise import BlockwiseNLP
-    from pycollo_b200 import examples
+    from examples import problems as examples
     from pycollo_b200.backend import lower_problem
     from pycollo_b200.mesh import PhaseMesh as OurPhaseMesh, PhaseMeshData
     from pycollo_b200.quadrature import Quadrature as OurQuadrature

@@ -43,11 +43,15 @@ NlpResult = SimpleNamespace
 def lower_problem(ocp, meshes=None, **structure_kwargs):
     """Symbolic lowering + structure + generated header for one mesh."""
     ir = build_ir(ocp)
-    pds = [analyse_phase(ph, ir.s) for ph in ir.phases]
-    ptd = analyse_point(ir)
+    # Settings.derivative_level == 1: first derivatives only -- no Hessian program is
+    # generated, compiled or exposed (the reference's live backend ignores the
+    # setting, SURVEY.md section 5; its cyipopt plumbing honours it, nlp.py:61)
+    second = int(getattr(ocp.settings, "derivative_level", 2)) >= 2
+    pds = [analyse_phase(ph, ir.s, second) for ph in ir.phases]
+    ptd = analyse_point(ir, second)
     if meshes is None:
         quad = Quadrature(ocp.settings.quadrature_method)
-        meshes = [PhaseMeshData(quad, ph.mesh, 2, 16) for ph in ocp.phases]
+        meshes = [PhaseMeshData(quad, ph.mesh, 2, 20) for ph in ocp.phases]
     S = NLPStructure(ir, pds, ptd, meshes,
                      prune=ocp.settings.prune_zero_quadrature_coefficients,
                      **structure_kwargs)
@@ -215,9 +219,9 @@ class IterationScaling:
             g = it.evaluate(_engine.EVAL_GRAD, x0)["grad"][0]
             g_norm = np.sqrt(np.sum(g ** 2))
             w = 1.0 if np.isclose(g_norm, 0.0) else 1.0 / g_norm
-        vals = it.evaluate(_engine.EVAL_JAC, x0)["jac"][0]
-        rows, _ = it.S.G_structure()
-        G_norm = np.sqrt(np.bincount(rows, vals * vals, minlength=it.S.num_c))
+        # row norms reduced on the device (pcx_jac_row_norms): num_c doubles come
+        # back instead of the nnz_G Jacobian values
+        G_norm = it.create_engine().jac_row_norms_host(x0)
         W = np.empty(self.backend.num_c)
         S = it.S
         for ph, t in zip(self.backend.ir.phases, S.ph):
@@ -238,12 +242,14 @@ def _interp1d_linear(x, y, x_new):
     """``scipy.interpolate.interp1d(x, y, bounds_error=False,
     fill_value="extrapolate")(x_new)`` as the reference calls it
     (``pycollo/iteration.py:128-134``): left bisection clipped to [1, M-1], then
-    ``slope * (x_new - x_lo) + y_lo``.  Same rule as ``pcx_interp_guess``."""
+    scipy's ``_call_linear`` formula ``((t - x_lo)/(x_hi - x_lo)) * y_hi +
+    ((x_hi - t)/(x_hi - x_lo)) * y_lo`` with the same operation order (bit-identical
+    results).  Same rule as ``pcx_interp_guess``; host mirror for deferred use."""
     x, y, x_new = (np.asarray(a, dtype=np.float64) for a in (x, y, x_new))
     hi = np.clip(np.searchsorted(x, x_new), 1, len(x) - 1)
     lo = hi - 1
-    slope = (y[hi] - y[lo]) / (x[hi] - x[lo])
-    return slope * (x_new - x[lo]) + y[lo]
+    den = x[hi] - x[lo]
+    return ((x_new - x[lo]) / den) * y[hi] + ((x[hi] - x_new) / den) * y[lo]
 
 
 class Iteration:
@@ -263,19 +269,45 @@ class Iteration:
 
     # -- initialise (iteration.py:69-79) ----------------------------------
     def initialise(self):
+        """Same stages as the reference: guess onto the mesh, counts/slices,
+        variable scaling, scaled guess, NLP generation (engine + J/c scaling),
+        bounds.  ``settings.defer_engine = True`` stops before anything touches
+        the device (structure-only use on a machine without a GPU: CPU tests,
+        table inspection); evaluation then starts with ``generate_nlp()``."""
         t0 = timer()
         low = lower_problem(self.ocp, self.mesh.p)
         self.low, self.S = low, low.S
-        self.interpolate_guess_to_mesh(self.prev_guess)
+        self.deferred = bool(getattr(self.ocp.settings, "defer_engine", False))
         self.create_variable_constraint_counts_slices()
         self.scaling = IterationScaling(self)
+        self.interpolate_guess_to_mesh(self.prev_guess)
         self.guess_x_tilde = self.scaling.scale_x(self.guess_x)
+        if not self.deferred:
+            self.generate_nlp()
         self.generate_bounds()
         self._time_initialise = timer() - t0
 
     def interpolate_guess_to_mesh(self, prev):
-        """Linear interpolation of the previous guess (``iteration.py:86-194``)."""
+        """Linear interpolation of the previous guess onto this mesh
+        (``iteration.py:86-194``): on the device (``pcx_interp_guess``, one thread
+        per variable and node, interp1d's own formula and rounding); the host
+        mirror below is only used by a deferred iteration."""
         self.guess_tau = self.mesh.tau
+        if not self.deferred:
+            parts = []
+            for ip in range(len(self.mesh.tau)):
+                parts += [np.ravel(prev.y[ip]), np.ravel(prev.u[ip]),
+                          np.ravel(prev.q[ip]), np.ravel(prev.t[ip])]
+            parts.append(np.ravel(prev.s))
+            x_prev = np.concatenate(parts).astype(np.float64)
+            self.guess_x = self.create_engine().interp_guess_host(
+                x_prev, [np.asarray(t, dtype=np.float64) for t in prev.tau],
+                [np.asarray(t, dtype=np.float64) for t in self.mesh.tau])
+            self.guess_y = [self.guess_x[sl].reshape(-1, len(tau))
+                            for sl, tau in zip(self.y_slices, self.mesh.tau)]
+            self.guess_u = [self.guess_x[sl].reshape(-1, len(tau))
+                            for sl, tau in zip(self.u_slices, self.mesh.tau)]
+            return
         parts = []
         self.guess_y, self.guess_u = [], []
         for ip, (tau, ptau) in enumerate(zip(self.mesh.tau, prev.tau)):
@@ -320,6 +352,21 @@ class Iteration:
         constraints are *variable bounds*, not rows of c (``:419-420``)."""
         S, ir = self.S, self.backend.ir
         sc = self.scaling
+        if not self.deferred:
+            # on the device (pcx_expand_bounds): OCP-level (lo, hi) pairs in, scaled
+            # mesh vectors out; c bounds are produced with W = 1 and scaled by the
+            # current W in the c_bnd_l / c_bnd_u properties
+            c_rows = []
+            for ph in ir.phases:
+                c_rows += [np.zeros((ph.n_y, 2)), ph.p_bnd.reshape(-1, 2), np.zeros((ph.n_q, 2))]
+            c_rows.append(ir.b_bnd.reshape(-1, 2))
+            y0 = np.vstack([ph.y_t0_bnd.reshape(-1, 2) for ph in ir.phases])
+            yF = np.vstack([ph.y_tF_bnd.reshape(-1, 2) for ph in ir.phases])
+            self.x_bnd_l, self.x_bnd_u, cl, cu = self.create_engine().expand_bounds_host(
+                self.backend.bounds.x_bnd, y0, yF, np.vstack(c_rows), sc.V_ocp, sc.r_ocp,
+                np.ones(self.backend.num_c))
+            self._c_bnd_unscaled = (cl, cu)
+            return
         lo = np.empty(S.num_x)
         hi = np.empty(S.num_x)
         for ph, t in zip(ir.phases, S.ph):
@@ -379,6 +426,9 @@ class Iteration:
                                     self.scaling.W_ocp, self.scaling.w)
 
     def evaluate(self, what, x, lam=None, sigma=None):
+        if (what & _engine.EVAL_HESS) and int(self.ocp.settings.derivative_level) < 2:
+            raise ValueError("derivative_level=1: no Hessian callback has been generated "
+                             "(set settings.derivative_level = 2 for exact Hessians)")
         return self.create_engine().eval_host(what, x, lam, sigma)
 
 
@@ -510,11 +560,17 @@ class Cuda:
             lagrange = np.zeros(it.S.num_c)
         return it.evaluate(_engine.EVAL_HESS, x, lagrange, obj_factor)["hess"][0]
 
+    def _need_second_derivatives(self):
+        if int(self.ocp.settings.derivative_level) < 2:
+            raise ValueError("derivative_level=1: no Hessian has been generated")
+
     def evaluate_H_structure(self):
+        self._need_second_derivatives()
         rows, cols = self._it().S.H_structure()
         return rows.copy(), cols.copy()
 
     def evaluate_H_num_nonzero(self):
+        self._need_second_derivatives()
         return int(self._it().S.nnz_h)
 
     def evaluate_H(self, x, obj_factor=1.0, lagrange=None):
@@ -524,9 +580,13 @@ class Cuda:
             (self.evaluate_H_nonzeros(x, obj_factor, lagrange), (rows, cols)),
             shape=(it.S.num_x, it.S.num_x))
 
-    def nlp_callbacks(self):
-        from .nlp import NlpCallbacks
-        return NlpCallbacks(self._it())
+    def nlp_callbacks(self, ordering="cyipopt", x_check="full"):
+        """cyipopt-style callback object (``pycollo/nlp.py:36-76``); without
+        ``hessian`` members when ``settings.derivative_level == 1``."""
+        from .nlp import NlpCallbacks, NlpCallbacksFirstOrder
+        cls = NlpCallbacks if int(self.ocp.settings.derivative_level) >= 2 \
+            else NlpCallbacksFirstOrder
+        return cls(self._it(), ordering, x_check)
 
     def solve_nlp(self):
         raise NotImplementedError(

@@ -199,12 +199,12 @@ __device__ __forceinline__ bool pcx_decode_slot(const PcxParams& p, const int ru
     const unsigned long long w = pcx_ld_keep(p.recipes + R.rec0 + u, keep);
     const u32 lo = (u32)w;
     if (lo >> RC_SKIP_BIT) return false;
-    const int a = (int)((w >> 32) & 0xffu);
-    const int local = (int)(w >> 40);
+    const int a = (int)((w >> RC_VAR_SHIFT) & 0xffu);
+    const int local = (int)((w >> RC_LOCAL_SHIFT) & ((1u << RC_LOCAL_BITS) - 1));
     const int Pa = R.tv[a + 1] - R.tv[a];
     const int e = lo & ((1u << RC_E_BITS) - 1);
     const int bi = (lo >> RC_B_SHIFT) & ((1u << RC_B_BITS) - 1);
-    const int mloc = (lo >> RC_M_SHIFT) & ((1u << RC_M_BITS) - 1);
+    const int mloc = (int)((w >> RC_M_SHIFT) & ((1u << RC_M_BITS) - 1));
     S.cc = cst[(lo >> RC_C_SHIFT) & ((1u << RC_C_BITS) - 1)];
     const bool prev = (lo >> RC_PREV_BIT) & 1u;
     S.bcoef = sB[bi];                                // 1.0 for plain slots
@@ -446,8 +446,8 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     double* sDP = sD + (WANT_G ? Ph::ND1V * nnp : 0);          // ND1V * (nsec + 1)
     const int nsp = nsec + 1;
     double* sDS = sDP + (WANT_G ? Ph::ND1V * nsp : 0);         // NDS * nnp
-    double* sLam = sDS + (WANT_G ? NDS * nnp : 0);             // NY * (nn + 16)
-    const int lam_stride = nn + 16;
+    double* sLam = sDS + (WANT_G ? NDS * nnp : 0);             // NY * (nn + PCX_LAM_HALO)
+    const int lam_stride = nn + PCX_LAM_HALO;
     double* sRed = sLam + (WANT_H ? NY * lam_stride : 0);      // T/32
     int* sSecNode = reinterpret_cast<int*>(sRed + T / 32);     // nsec+2 (prev first)
     int* sSecOrder = sSecNode + (nsec + 2);                    // nsec+1 (prev first)
@@ -793,6 +793,20 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
 // reduction is selected only the first and last tile of each phase signal, so
 // the pass is off the kernel's critical path.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pcx_ld_acquire_sys(const unsigned long long* ptr) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long pcx_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// a peer that never arrives (failed launch on another rank) must not hang this
+// GPU: the spin gives up after 5 s and leaves 1 in the engine's status word
+#define PCX_EXCHANGE_TIMEOUT_NS 5000000000ull
+
 __device__ __forceinline__ u32 pcx_ld_acquire(const u32* ptr) {
     u32 v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
@@ -954,8 +968,22 @@ __device__ __noinline__ void pcx_border(const PcxParams& p, const int inst, doub
             xb[(PCX_BV_PTVAL - 1) + (i - PCX_BV_IRR)] = bv[i];
     } else if (mode == 3) {
         // fused exchange over peer memory: write this rank's share into the
-        // border rank's buffer, make it visible system-wide, publish the epoch
-        double* mine = p.peer_xbuf + ((i64)p.rank * p.batch + inst) * p.bv_size;
+        // border rank's buffer, make it visible system-wide, publish the epoch.
+        // Shares are double-buffered by epoch parity; before a slot is reused
+        // the border rank must have consumed its previous content (epoch - 2).
+        const int par = (int)(p.epoch & 1ull);
+        if (tid == 0 && p.epoch > 2ull) {
+            unsigned long long done, t0 = pcx_globaltimer();
+            do {
+                done = pcx_ld_acquire_sys(p.peer_done + inst);
+                if (done + 2ull < p.epoch) {
+                    __nanosleep(200);
+                    if (pcx_globaltimer() - t0 > PCX_EXCHANGE_TIMEOUT_NS) { atomicExch(p.status, 1u); break; }
+                }
+            } while (done + 2ull < p.epoch);
+        }
+        __syncthreads();
+        double* mine = p.peer_xbuf + (((i64)p.rank * 2 + par) * p.batch + inst) * p.bv_size;
         for (int i = 1 + tid; i < PCX_BV_PTVAL; i += T) mine[i - 1] = bv[i];
         for (int i = PCX_BV_IRR + tid; i < p.bv_size; i += T)
             mine[(PCX_BV_PTVAL - 1) + (i - PCX_BV_IRR)] = bv[i];
@@ -965,25 +993,31 @@ __device__ __noinline__ void pcx_border(const PcxParams& p, const int inst, doub
             asm volatile("st.release.sys.global.u64 [%0], %1;"
                          :: "l"(p.peer_flags + (i64)p.rank * p.batch + inst), "l"(p.epoch) : "memory");
         if (p.rank == p.border_rank) {
-            // wait for every rank's share of this evaluation, then sum in rank
-            // order (deterministic) and apply the border map
-            if (tid < p.world) {
-                unsigned long long seen;
+            // wait for every rank's share of this evaluation (any number of ranks,
+            // whatever the CTA size), then sum in rank order (deterministic) and
+            // apply the border map
+            for (int r = tid; r < p.world; r += T) {
+                unsigned long long seen, t0 = pcx_globaltimer();
                 do {
-                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];"
-                                 : "=l"(seen) : "l"(p.peer_flags + (i64)tid * p.batch + inst) : "memory");
-                    if (seen < p.epoch) __nanosleep(200);
+                    seen = pcx_ld_acquire_sys(p.peer_flags + (i64)r * p.batch + inst);
+                    if (seen < p.epoch) {
+                        __nanosleep(200);
+                        if (pcx_globaltimer() - t0 > PCX_EXCHANGE_TIMEOUT_NS) { atomicExch(p.status, 1u); break; }
+                    }
                 } while (seen < p.epoch);
             }
             __syncthreads();
             for (int i = tid; i < xlen; i += T) {
                 double acc = 0.0;
                 for (int r = 0; r < p.world; ++r)
-                    acc += __ldcv(p.peer_xbuf + ((i64)r * p.batch + inst) * p.bv_size + i);
+                    acc += __ldcv(p.peer_xbuf + (((i64)r * 2 + par) * p.batch + inst) * p.bv_size + i);
                 const int j = i < PCX_BV_PTVAL - 1 ? 1 + i : PCX_BV_IRR + (i - (PCX_BV_PTVAL - 1));
                 bv[j] = acc;
             }
             __syncthreads();
+            if (tid == 0)
+                asm volatile("st.release.sys.global.u64 [%0], %1;"
+                             :: "l"(p.peer_done + inst), "l"(p.epoch) : "memory");
             pcx_border_map(p, inst, bv, sRS, true, nullptr);
         }
     } else {

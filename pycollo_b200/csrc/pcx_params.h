@@ -14,16 +14,24 @@ typedef long long i64;
 typedef unsigned int u32;
 
 // recipe word layout -- keep in sync with pycollo_b200/structure.py
+// low word: staged row (9), quadrature-table index (13), constant index (7),
+// PREV / PLAIN / SKIP; high word: variable (8), slot inside the variable's
+// period (18), node inside the section (5: up to 20 nodes per section)
 #define RC_E_BITS 9
-#define RC_B_BITS 9
-#define RC_M_BITS 4
+#define RC_B_BITS 13
 #define RC_C_BITS 7
 #define RC_B_SHIFT 9
-#define RC_M_SHIFT 18
 #define RC_C_SHIFT 22
 #define RC_PREV_BIT 29
 #define RC_PLAIN_BIT 30
 #define RC_SKIP_BIT 31
+#define RC_VAR_SHIFT 32
+#define RC_LOCAL_SHIFT 40
+#define RC_LOCAL_BITS 18
+#define RC_M_SHIFT 58
+#define RC_M_BITS 5
+// halo of the defect-multiplier tile: rows of the previous section (< 20)
+#define PCX_LAM_HALO 24
 
 struct PcxParams {
     // per-call
@@ -46,13 +54,17 @@ struct PcxParams {
     int tile_begin, tile_count, border_mode;
     double* xbuf;           // (batch, xbuf_len): [reductions | end-node values]
     // border_mode 3: the exchange is fused into the kernel over peer memory
-    // (NVLink).  Every rank's border CTA writes its share into slot `rank` of
-    // peer_xbuf (world x batch x bv_size doubles, in the border rank's memory)
-    // and then publishes `epoch` in peer_flags[rank]; the border rank waits for
-    // all flags, sums the shares in rank order and applies the border map.
-    double* peer_xbuf; unsigned long long* peer_flags;
+    // (NVLink).  Every rank's border CTA writes its share into slot
+    // (rank, epoch & 1) of peer_xbuf (world x 2 x batch x bv_size doubles, in the
+    // border rank's memory) and then publishes `epoch` in peer_flags[rank]; the
+    // border rank waits for all flags, sums the shares in rank order, applies the
+    // border map and publishes `epoch` in peer_done[inst].  A writer reuses a
+    // slot (same parity, two evaluations later) only after the border rank has
+    // consumed it: a rank can run at most two evaluations ahead.
+    double* peer_xbuf; unsigned long long* peer_flags; unsigned long long* peer_done;
     unsigned long long epoch;
     int rank, world, border_rank, pad1;
+    u32* status;            // sticky device-side error word (0 = ok; 1 = exchange timeout)
     // tiles
     const i64* tile_desc;   // 8 per tile: phase,k0,k1,node0,nn,run0,run1,-
     const int* run_slo; const int* run_shi; const int* run_type;

@@ -59,7 +59,9 @@ class PhaseDerivs:
                  [(e, j + self.NV) for e, j in self.d1s]) if aa == a}
 
 
-def analyse_phase(ph, s_syms) -> PhaseDerivs:
+def analyse_phase(ph, s_syms, second=True) -> PhaseDerivs:
+    """``second=False`` (``Settings.derivative_level == 1``): no second derivatives
+    are formed, so no Hessian program is generated or compiled."""
     v = list(ph.y) + list(ph.u)
     allv = v + list(s_syms)
     fns = list(ph.f) + list(ph.p) + list(ph.g)
@@ -83,7 +85,7 @@ def analyse_phase(ph, s_syms) -> PhaseDerivs:
             else:
                 pd.d1s.append((e, a - NV))
                 pd.d1s_expr.append(da)
-            for b in range(a, len(allv)):
+            for b in range(a, len(allv) if second else a):
                 if allv[b] not in da.free_symbols:
                     continue
                 dab = sym.diff(da, allv[b])
@@ -99,8 +101,9 @@ def analyse_phase(ph, s_syms) -> PhaseDerivs:
     pd.h2vv = sorted(vv, key=lambda t: (t[1], t[0]))   # column-major: by b then a
     pd.h2vs = sorted(vs, key=lambda t: (t[1], t[0]))
     pd.h2ss = sorted(ss, key=lambda t: (t[1], t[0]))
-    pd.htv = sorted({a for e, a in pd.d1v if fam[e] in "di"})
-    pd.hts = sorted({j for e, j in pd.d1s if fam[e] in "di"})
+    if second:
+        pd.htv = sorted({a for e, a in pd.d1v if fam[e] in "di"})
+        pd.hts = sorted({j for e, j in pd.d1s if fam[e] in "di"})
     return pd
 
 
@@ -114,7 +117,7 @@ class PointDerivs:
     pairs: list               # (a, b) union over e, a <= b
 
 
-def analyse_point(ir) -> PointDerivs:
+def analyse_point(ir, second=True) -> PointDerivs:
     pts = list(ir.point_symbols)
     fns = [ir.J] + list(ir.b)
     d1, d1e, d2, pairs = [], [], [], set()
@@ -127,7 +130,7 @@ def analyse_point(ir) -> PointDerivs:
                 continue
             d1.append((e, a))
             d1e.append(da)
-            for b in range(a, len(pts)):
+            for b in range(a, len(pts) if second else a):
                 if pts[b] not in da.free_symbols:
                     continue
                 dab = sym.diff(da, pts[b])

@@ -44,6 +44,12 @@ class _Spec(ctypes.Structure):
                 ("tables", ctypes.POINTER(_Table))]
 
 
+class _Args(ctypes.Structure):
+    """``pcx_args``: one argument set of ``pcx_eval_many``."""
+    _fields_ = [(k, ctypes.c_void_p) for k in
+                ("x", "lam", "sigma", "f", "grad", "c", "dy", "jac", "hess")]
+
+
 def load_library(rebuild=False):
     """Load (building first if stale and nvcc is present) the C-ABI library."""
     global _LIB
@@ -97,6 +103,13 @@ def load_library(rebuild=False):
     lib.pcx_refit_size.argtypes = [vp, ctypes.POINTER(i64)]
     lib.pcx_mesh_error.argtypes = [vp, dp, dp, dp, dp, i32, vp]
     lib.pcx_mesh_error_sizes.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.pcx_structure_jac.argtypes = [vp, i32, dp, dp, dp]
+    lib.pcx_structure_hess.argtypes = [vp, i32, dp, dp, dp]
+    lib.pcx_jac_row_norms.argtypes = [vp, dp, dp, i32, vp]
+    lib.pcx_expand_bounds.argtypes = [vp] + [dp] * 11 + [i32, vp]
+    lib.pcx_eval_many.argtypes = [vp, i32, ctypes.POINTER(_Args), i32, i32, vp, i32,
+                                  ctypes.POINTER(ctypes.c_float)]
+    lib.pcx_status.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
     _LIB = lib
     return lib
 
@@ -196,10 +209,12 @@ def build_tables(S, layouts):
         nqt = irp.n_q + irp.n_t
         rd[ip, :12] = (ph.x_off, ph.N, ph.K, pd.NY, NU, nqt, ph.dy_off, ph.sec_off + ip,
                        ph.sec_off, xph, ph.t_cols[0], ph.t_cols[1])
+        rd[ip, 12:15] = (ph.c_off, irp.n_p, irp.n_q)            # pcx_expand_bounds
         rc[ip] = ph.t_const
         xph += pd.NV * (ph.N + ph.K) + nqt
         work += ph.K * pd.NV
     rd[-1, :5] = (S.s_off, S.NS, xph, xph + S.NS, work)
+    rd[-1, 5:7] = (S.NB, S.b_off)
     t["refit_desc"] = rd.ravel()
     t["refit_const"] = rc.ravel()
     return {k: np.ascontiguousarray(v, dtype=_TABLE_DTYPES[k]) for k, v in t.items()}
@@ -265,7 +280,7 @@ def smem_bytes(S, layouts, threads):
         nds = sum(1 for e, _ in pd.d1s if pd.fam[e] == "d")
         dbl = (len(S.btab) + SS + 1 + (pd.NY + len(pd.d1v) + nds) * (NN | 1)
                + len(pd.d1v) * (SS + 1)
-               + pd.NY * (NN + 16) + threads // 32 + 2)
+               + pd.NY * (NN + 24) + threads // 32 + 2)      # PCX_LAM_HALO
         ints = (SS + 2) + (SS + 1) + NN + 2 * (SS + 1) + 8
         best = max(best, 8 * dbl + 4 * ints)
     best = max(best, 8 * (32 + S.bv_size))      # border pass: scratch + BV
@@ -285,7 +300,12 @@ def _ptr(a):
 class Engine:
     """One compiled problem on one mesh on one device (wraps ``pcx_engine``)."""
 
-    def __init__(self, S, layouts, header, *, batch=1, device=0, min_blocks=None):
+    # above this many Jacobian non-zeros the int64 patterns (16 B per entry, host
+    # copies inside the library) are only handed over on request
+    STRUCTURE_AUTO_LIMIT = 50_000_000
+
+    def __init__(self, S, layouts, header, *, batch=1, device=0, min_blocks=None,
+                 structure=None):
         self.lib = load_library()
         self.S, self.layouts = S, layouts
         self.batch = int(batch)
@@ -299,7 +319,15 @@ class Engine:
         if self.smem > 227 * 1024:
             raise PcxError(f"tile needs {self.smem} B of shared memory (> 227 KB)")
         n = self.lib.pcx_table_count()
-        arr = (_Table * n)()
+        if structure is None:
+            structure = S.nnz_g <= self.STRUCTURE_AUTO_LIMIT
+        self.has_structure = bool(structure)
+        extra = []
+        if structure:       # patterns for pcx_structure_* / pcx_jac_row_norms (host side)
+            gr, gc = S.G_structure()
+            hr, hc = S.H_structure()
+            extra = [(b"g_rows", gr), (b"g_cols", gc), (b"h_rows", hr), (b"h_cols", hc)]
+        arr = (_Table * (n + len(extra)))()
         self._keep = []
         for i in range(n):
             name = self.lib.pcx_table_name(i)
@@ -307,6 +335,11 @@ class Engine:
             assert a.itemsize == self.lib.pcx_table_elem_size(i), name
             self._keep.append(a)
             arr[i] = _Table(name, a.ctypes.data_as(ctypes.c_void_p), a.nbytes)
+        for k, (name, a) in enumerate(extra):
+            a = np.ascontiguousarray(a, dtype=np.int64)
+            self._keep.append(a)
+            arr[n + k] = _Table(name, a.ctypes.data_as(ctypes.c_void_p), a.nbytes)
+        n += len(extra)
         self._header = header.encode()
         spec = _Spec(device=self.device, threads=self.threads, batch=self.batch,
                      num_tiles=S.num_tiles, nvmax=S.NVMAX,
@@ -380,6 +413,70 @@ class Engine:
             _ptr(out.get("grad")), _ptr(out.get("c")), _ptr(out.get("dy")),
             _ptr(out.get("jac")), _ptr(out.get("hess")), PCX_HOST, None), "pcx_eval")
         return out
+
+    # -- structure / scaling / bounds through the C ABI -------------------------
+    _ORDERS = {"ccs": 0, "triu_ccs": 0, "native": 0, "row_major": 1, "tril_row_major": 1}
+
+    def _structure(self, fn, nnz, order):
+        rows, cols, perm = (np.empty(nnz, dtype=np.int64) for _ in range(3))
+        self._check(fn(self.h, self._ORDERS[order], _ptr(rows), _ptr(cols), _ptr(perm)),
+                    fn.__name__)
+        return rows, cols, perm
+
+    def structure_jac(self, order="ccs"):
+        """``pcx_structure_jac``: (rows, cols, perm); ``values[perm]`` is the order."""
+        return self._structure(self.lib.pcx_structure_jac, self.S.nnz_g, order)
+
+    def structure_hess(self, order="triu_ccs"):
+        return self._structure(self.lib.pcx_structure_hess, self.S.nnz_h, order)
+
+    def jac_row_norms_host(self, x):
+        """``pcx_jac_row_norms``: ||G[i, :]||_2 per constraint row, reduced on the
+        device (``pycollo/scaling.py:392-396`` without the dense matrix)."""
+        S, B = self.S, self.batch
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(B, S.num_x)
+        out = np.empty((B, S.num_c))
+        self._check(self.lib.pcx_jac_row_norms(self.h, _ptr(x), _ptr(out), PCX_HOST, None),
+                    "pcx_jac_row_norms")
+        return out[0] if B == 1 else out
+
+    def expand_bounds_host(self, ocp_x_bnd, y_t0_bnd, y_tF_bnd, ocp_c_bnd, V_ocp, r_ocp, W_ocp):
+        """``pcx_expand_bounds``: scaled (x_lo, x_hi, c_lo, c_hi) on the mesh."""
+        S = self.S
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        xl, xh = np.empty(S.num_x), np.empty(S.num_x)
+        cl, ch = np.empty(S.num_c), np.empty(S.num_c)
+        args = [f(ocp_x_bnd), f(y_t0_bnd), f(y_tF_bnd), f(ocp_c_bnd), f(V_ocp), f(r_ocp), f(W_ocp)]
+        self._check(self.lib.pcx_expand_bounds(
+            self.h, *[_ptr(a) if a.size else None for a in args], _ptr(xl), _ptr(xh),
+            _ptr(cl), _ptr(ch), PCX_HOST, None), "pcx_expand_bounds")
+        return xl, xh, cl, ch
+
+    def make_args(self, sets):
+        """Argument sets for ``eval_many`` from dicts of device tensors / pointers."""
+        arr = (_Args * len(sets))()
+        for i, d in enumerate(sets):
+            for k in ("x", "lam", "sigma", "f", "grad", "c", "dy", "jac", "hess"):
+                p = _ptr(d.get(k))
+                setattr(arr[i], k, p.value if p is not None else None)
+        arr.keepalive = sets
+        return arr
+
+    def eval_many(self, what, args, count, stream=None, gate=True, timed=True):
+        """``pcx_eval_many``: ``count`` launches enqueued from C, cycling through the
+        argument sets; returns the device time in ms between the first launch and
+        the end of the last one (CUDA events on ``stream``) when ``timed``."""
+        ms = ctypes.c_float(0.0)
+        self._check(self.lib.pcx_eval_many(
+            self.h, what, args, len(args), int(count),
+            ctypes.c_void_p(stream) if stream else None, 1 if gate else 0,
+            ctypes.byref(ms) if timed else None), "pcx_eval_many")
+        return float(ms.value)
+
+    def status(self):
+        code = ctypes.c_int(0)
+        self._check(self.lib.pcx_status(self.h, ctypes.byref(code)), "pcx_status")
+        return int(code.value)
 
     # -- one mesh over several GPUs (include/pcx.h, SURVEY.md section 8(e)) ----
     def set_shard(self, tile_begin, tile_end):

@@ -37,7 +37,7 @@ class MeshErrorEvaluator:
     """One engine on the ph mesh of an iteration's mesh; reusable for any number
     of ``x_ph`` vectors (and ``batch`` of them per call)."""
 
-    def __init__(self, ocp, mesh, batch=1, device=0, collocation_points_max=16):
+    def __init__(self, ocp, mesh, batch=1, device=0, collocation_points_max=21):
         from .backend import lower_problem
         self.ph_mesh = create_ph_mesh(mesh, 2, collocation_points_max)
         self.low = lower_problem(ocp, self.ph_mesh.p)

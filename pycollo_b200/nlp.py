@@ -7,120 +7,207 @@ explicit) IPOPT plumbing: ``IPOPTProblem`` in ``pycollo/nlp.py:36-76`` --
 ``hessianstructure()``, ``intermediate(...)``.  That path orders the Jacobian
 row-major and uses the *lower* triangle of the Hessian
 (``pycollo/iteration.py:930-933, 965-968, 1057``), whereas the engine stores the
-live backend's CasADi order (CCS / upper triangle).  The two fixed permutations
-are computed once here.
+live backend's CasADi order (CCS / upper triangle); the fixed permutation comes
+from ``pcx_structure_jac(PCX_ORDER_ROW_MAJOR)`` and is applied on the device.
+
+An NLP solver asks for f, grad f, c and the Jacobian at the SAME iterate and
+then for the Hessian there: the object caches by iterate.  The first callback
+that sees a new x ships it to the device once (pinned staging) and evaluates
+f, grad f and c in one fused launch; ``jacobian`` and ``hessian`` reuse the
+device-resident x (``hessian`` ships only the multipliers).  Nothing is
+recomputed and x crosses PCIe once per iterate.
+
+With ``derivative_level=1`` the object has no ``hessian`` / ``hessianstructure``
+members at all (``NlpCallbacksFirstOrder``), which is how a cyipopt host selects
+its limited-memory quasi-Newton mode (``pycollo/nlp.py:61-62``).
 """
 from __future__ import annotations
+
+import ctypes
 
 import numpy as np
 
 from . import engine as _engine
 
+_LIBC = ctypes.CDLL(None)
+_LIBC.memcmp.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
 
-class NlpCallbacks:
-    def __init__(self, iteration, ordering="cyipopt"):
+
+class NlpCallbacksFirstOrder:
+    """objective / gradient / constraints / jacobian (+ structure)."""
+
+    def __init__(self, iteration, ordering="cyipopt", x_check="full"):
         self.it = iteration
         S = iteration.S
-        gr, gc = S.G_structure()
-        hr, hc = S.H_structure()
-        if ordering == "cyipopt":
-            self.g_perm = np.lexsort((gc, gr))             # row-major
-            self.h_perm = np.lexsort((hr, hc))             # tril, row-major
-            self._g_struct = (gr[self.g_perm], gc[self.g_perm])
-            # lower triangle: swap (row, col) of the stored upper triangle
-            self._h_struct = (hc[self.h_perm], hr[self.h_perm])
-        elif ordering == "casadi":
-            self.g_perm = np.arange(len(gr))
-            self.h_perm = np.arange(len(hr))
-            self._g_struct = (gr, gc)
-            self._h_struct = (hr, hc)
-        else:
+        if ordering not in ("cyipopt", "casadi"):
             raise ValueError("ordering must be 'cyipopt' or 'casadi'")
-        self.ordering = ordering
-        self.num_evals = dict(objective=0, gradient=0, constraints=0,
-                              jacobian=0, hessian=0)
-        self._fast = None
+        if x_check not in ("full", "sampled"):
+            raise ValueError("x_check must be 'full' or 'sampled'")
+        self.ordering, self.x_check = ordering, x_check
+        # a deferred iteration (structure-only use, no device) has no engine yet
+        eng = None if getattr(iteration, "deferred", False) else iteration.create_engine()
+        order = "row_major" if ordering == "cyipopt" else "ccs"
+        if eng is not None and eng.has_structure:      # from the C ABI (pcx_structure_*)
+            gr, gc, self.g_perm = eng.structure_jac(order)
+            hr, hc, self.h_perm = eng.structure_hess(
+                "tril_row_major" if ordering == "cyipopt" else "triu_ccs")
+        else:                                          # host tables (same rule)
+            gr, gc = S.G_structure()
+            hr, hc = S.H_structure()
+            if ordering == "cyipopt":
+                self.g_perm = np.lexsort((gc, gr))
+                gr, gc = gr[self.g_perm], gc[self.g_perm]
+                hr, hc = hc, hr
+            else:
+                self.g_perm = np.arange(len(gr))
+            self.h_perm = np.arange(len(hr))
+        self._g_struct, self._h_struct = (gr, gc), (hr, hc)
+        self._identity_g = bool(np.array_equal(self.g_perm, np.arange(len(self.g_perm))))
+        self.num_evals = dict(objective=0, gradient=0, constraints=0, jacobian=0, hessian=0)
+        self.num_launches = dict(point=0, jacobian=0, hessian=0)
+        self.num_x_uploads = 0
+        self._b = None
+        self._have_x = False
+        self._fresh = set()
 
-    # -- the hot callbacks: pinned staging, device-side permutation ------------
-    def _fast_path(self):
-        """Persistent buffers for ``jacobian`` / ``hessian``: pinned host staging for
-        x, lam and the values (copies at PCIe speed instead of pageable-memory
-        speed), and the cyipopt permutation applied on the device (``pcx_gather``)
-        instead of a 4-million-element numpy fancy index per call."""
-        if self._fast is None:
+    # -- persistent buffers ---------------------------------------------------------
+    def _buffers(self):
+        """Pinned host staging for x, lam and every result (copies at PCIe speed,
+        results handed out as views -- valid until the next call of the same kind),
+        device buffers, the permutation on the device."""
+        if self._b is None:
             import torch
             it = self.it
             S = it.S
             eng = it.create_engine()
             dev = torch.device("cuda", it.device)
             f64 = dict(dtype=torch.float64)
-            b = dict(
-                torch=torch, eng=eng, stream=torch.cuda.Stream(device=dev),
-                hx=torch.empty(S.num_x, **f64).pin_memory(), dx=torch.empty(S.num_x, device=dev, **f64),
-                hl=torch.empty(S.num_c, **f64).pin_memory(), dl=torch.empty(S.num_c, device=dev, **f64),
-                ds=torch.ones(1, device=dev, **f64), hs=torch.ones(1, **f64).pin_memory(),
-                dg=torch.empty(S.nnz_g, device=dev, **f64), dgp=torch.empty(S.nnz_g, device=dev, **f64),
-                hg=torch.empty(S.nnz_g, **f64).pin_memory(),
-                dh=torch.empty(S.nnz_h, device=dev, **f64), dhp=torch.empty(S.nnz_h, device=dev, **f64),
-                hh=torch.empty(S.nnz_h, **f64).pin_memory(),
-                gperm=torch.from_numpy(np.ascontiguousarray(self.g_perm, dtype=np.int64)).to(dev),
-                hperm=torch.from_numpy(np.ascontiguousarray(self.h_perm, dtype=np.int64)).to(dev))
-            self._fast = b
-        return self._fast
+            pin = lambda n: torch.empty(n, **f64).pin_memory()
+            devb = lambda n: torch.empty(n, device=dev, **f64)
+            b = dict(torch=torch, eng=eng, stream=torch.cuda.Stream(device=dev),
+                     hx=pin(S.num_x), dx=devb(S.num_x), hl=pin(S.num_c), dl=devb(S.num_c),
+                     hs=torch.ones(1, **f64).pin_memory(), ds=torch.ones(1, device=dev, **f64),
+                     hf=pin(1), df=devb(1), hgrad=pin(S.num_x), dgrad=devb(S.num_x),
+                     hc=pin(S.num_c), dc=devb(S.num_c),
+                     dg=devb(S.nnz_g), dgp=devb(S.nnz_g), hg=pin(S.nnz_g),
+                     dh=devb(S.nnz_h), hh=pin(S.nnz_h),
+                     gperm=torch.from_numpy(np.ascontiguousarray(self.g_perm, dtype=np.int64)).to(dev))
+            b["hx_np"] = b["hx"].numpy()
+            self._b = b
+        return self._b
 
-    def _values(self, what, x, lagrange=None, obj_factor=1.0):
-        b = self._fast_path()
-        torch, eng, st = b["torch"], b["eng"], b["stream"]
-        jac = what == _engine.EVAL_JAC
-        b["hx"].numpy()[:] = x
-        with torch.cuda.stream(st):
-            b["dx"].copy_(b["hx"], non_blocking=True)
-            if not jac:
-                b["hl"].numpy()[:] = lagrange
-                b["hs"][0] = float(obj_factor)
-                b["dl"].copy_(b["hl"], non_blocking=True)
-                b["ds"].copy_(b["hs"], non_blocking=True)
-            raw, perm, out, host = (b["dg"], b["gperm"], b["dgp"], b["hg"]) if jac else \
-                (b["dh"], b["hperm"], b["dhp"], b["hh"])
-            if jac:
-                eng.eval_ptr(what, b["dx"], jac=raw, stream=st.cuda_stream)
-            else:
-                eng.eval_ptr(what, b["dx"], lam=b["dl"], sigma=b["ds"], hess=raw, stream=st.cuda_stream)
-            if self.ordering == "cyipopt":
-                eng.gather(raw, perm, raw.numel(), out, stream=st.cuda_stream)
-            else:
-                out = raw
-            host.copy_(out, non_blocking=True)
-        st.synchronize()
-        return host.numpy()          # pinned staging: valid until the next call of this kind
+    # -- iterate cache ----------------------------------------------------------------
+    def _same_x(self, x, b):
+        if not self._have_x:
+            return False
+        hx = b["hx_np"]
+        if x.shape != hx.shape:
+            return False
+        if self.x_check == "sampled":
+            step = max(1, x.size // 4096)
+            return bool(np.array_equal(x[::step], hx[::step]) and x[-1] == hx[-1])
+        return _LIBC.memcmp(x.ctypes.data, hx.ctypes.data, hx.nbytes) == 0
 
-    def objective(self, x):
+    def _touch(self, x, new_x=None):
+        """Make ``x`` the device-resident iterate.  ``new_x`` (the flag IPOPT's own
+        TNLP interface carries) skips the comparison: True = x changed, False =
+        same x as the previous callback."""
+        b = self._buffers()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if new_x is None:
+            new_x = not self._same_x(x, b)
+        if new_x or not self._have_x:
+            torch, st = b["torch"], b["stream"]
+            np.copyto(b["hx_np"], x)
+            with torch.cuda.stream(st):
+                b["dx"].copy_(b["hx"], non_blocking=True)
+            self._have_x = True
+            self._fresh.clear()
+            self.num_x_uploads += 1
+        return b
+
+    def _point(self, x, new_x):
+        """f, grad f and c at the iterate: one fused launch."""
+        b = self._touch(x, new_x)
+        if "point" not in self._fresh:
+            torch, eng, st = b["torch"], b["eng"], b["stream"]
+            with torch.cuda.stream(st):
+                eng.eval_ptr(_engine.EVAL_F | _engine.EVAL_GRAD | _engine.EVAL_C, b["dx"],
+                             f=b["df"], grad=b["dgrad"], c=b["dc"], stream=st.cuda_stream)
+                b["hf"].copy_(b["df"], non_blocking=True)
+                b["hgrad"].copy_(b["dgrad"], non_blocking=True)
+                b["hc"].copy_(b["dc"], non_blocking=True)
+            st.synchronize()
+            self._fresh.add("point")
+            self.num_launches["point"] += 1
+        return b
+
+    def objective(self, x, new_x=None):
         self.num_evals["objective"] += 1
-        return float(self.it.evaluate(_engine.EVAL_F, x)["f"][0])
+        return float(self._point(x, new_x)["hf"][0])
 
-    def gradient(self, x):
+    def gradient(self, x, new_x=None):
         self.num_evals["gradient"] += 1
-        return self.it.evaluate(_engine.EVAL_GRAD, x)["grad"][0]
+        return self._point(x, new_x)["hgrad"].numpy()
 
-    def constraints(self, x):
+    def constraints(self, x, new_x=None):
         self.num_evals["constraints"] += 1
-        return self.it.evaluate(_engine.EVAL_C, x)["c"][0]
+        return self._point(x, new_x)["hc"].numpy()
 
-    def jacobian(self, x):
+    def jacobian(self, x, new_x=None):
         self.num_evals["jacobian"] += 1
-        return self._values(_engine.EVAL_JAC, x)
+        b = self._touch(x, new_x)
+        if "jac" not in self._fresh:
+            torch, eng, st = b["torch"], b["eng"], b["stream"]
+            with torch.cuda.stream(st):
+                eng.eval_ptr(_engine.EVAL_JAC, b["dx"], jac=b["dg"], stream=st.cuda_stream)
+                src = b["dg"]
+                if not self._identity_g:
+                    eng.gather(b["dg"], b["gperm"], b["dg"].numel(), b["dgp"],
+                               stream=st.cuda_stream)
+                    src = b["dgp"]
+                b["hg"].copy_(src, non_blocking=True)
+            st.synchronize()
+            self._fresh.add("jac")
+            self.num_launches["jacobian"] += 1
+        return b["hg"].numpy()
 
     def jacobianstructure(self):
         return self._g_struct
-
-    def hessian(self, x, lagrange, obj_factor):
-        self.num_evals["hessian"] += 1
-        return self._values(_engine.EVAL_HESS, x, lagrange, obj_factor)
-
-    def hessianstructure(self):
-        return self._h_struct
 
     def intermediate(self, alg_mod, iter_count, obj_value, inf_pr, inf_du, mu,
                      d_norm, regularization_size, alpha_du, alpha_pr, ls_trials):
         self.last_iterate = dict(iter_count=iter_count, obj_value=obj_value,
                                  inf_pr=inf_pr, inf_du=inf_du)
+
+
+class NlpCallbacks(NlpCallbacksFirstOrder):
+    """+ ``hessian(x, lagrange, obj_factor)`` / ``hessianstructure()``
+    (``derivative_level=2``).  The lower triangle in row-major order IS the
+    engine's upper triangle in CCS order with rows and columns swapped, so the
+    Hessian values need no permutation in either ordering."""
+
+    def __init__(self, iteration, ordering="cyipopt", x_check="full"):
+        if int(iteration.ocp.settings.derivative_level) < 2:
+            raise ValueError("derivative_level=1: use NlpCallbacksFirstOrder "
+                             "(no Hessian callback exists)")
+        super().__init__(iteration, ordering, x_check)
+
+    def hessian(self, x, lagrange, obj_factor, new_x=None):
+        self.num_evals["hessian"] += 1
+        b = self._touch(x, new_x)
+        torch, eng, st = b["torch"], b["eng"], b["stream"]
+        np.copyto(b["hl"].numpy(), np.asarray(lagrange, dtype=np.float64))
+        b["hs"][0] = float(obj_factor)
+        with torch.cuda.stream(st):
+            b["dl"].copy_(b["hl"], non_blocking=True)
+            b["ds"].copy_(b["hs"], non_blocking=True)
+            eng.eval_ptr(_engine.EVAL_HESS, b["dx"], lam=b["dl"], sigma=b["ds"], hess=b["dh"],
+                         stream=st.cuda_stream)
+            b["hh"].copy_(b["dh"], non_blocking=True)
+        st.synchronize()
+        self.num_launches["hessian"] += 1
+        return b["hh"].numpy()
+
+    def hessianstructure(self):
+        return self._h_struct

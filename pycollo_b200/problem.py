@@ -95,6 +95,7 @@ class Settings:
         self.check_nlp_functions = False
         # engine-specific (new; no reference counterpart)
         self.prune_zero_quadrature_coefficients = True
+        self.defer_engine = False        # True: initialise() stops before the device
         for key, value in kwargs.items():
             setattr(self, key, value)
 

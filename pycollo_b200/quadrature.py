@@ -1,8 +1,22 @@
 """Collocation point sets, quadrature weights and integration blocks.
 
 Host-side, once-per-settings tables that end up as device-resident constants
-of the CUDA engine.  Written from the mathematical
-definitions, not from the reference's generator:
+of the CUDA engine.
+
+Two constructions are offered (``Quadrature(method, tables=...)``):
+
+``tables="reference"`` (default) reproduces the NUMERICS of the reference's
+generator (``pycollo/quadrature.py:116-261``): points from numpy's Legendre
+companion-matrix roots, the closed-form weights, and the Butcher rows as the
+``numpy.linalg.solve`` solution of the simplifying-condition system
+``sum_i w_i c_i^k a_ij = w_j (1 - c_j^(k+1))/(k+1) - w_last w_j`` assembled in the
+same unknown/equation order -- so the tables are the reference's to the last
+bit (``tests/test_quadrature_mesh.py`` against tables produced by executing the
+reference, orders 2..20), including the digits that ill-conditioned solve loses
+at high order (1.3e-12 at order 10).  Parity is with the reference, not with
+the mathematics.
+
+``tables="exact"`` is written from the mathematical definitions instead:
 
 * Lobatto (LGL) points are the roots of ``P'_{n-1}`` plus the two ends, found by
   Newton iteration on the Legendre recurrence; weights ``1/(n(n-1)P_{n-1}(x)^2)``
@@ -127,6 +141,48 @@ def _collocation_matrix(c):
     return A
 
 
+def _reference_numerics(n, method):
+    """Points, weights and Butcher array with the floating-point operations of
+    the reference's generators (``pycollo/quadrature.py:116-163`` Radau,
+    ``:189-246`` Lobatto), so that every entry is bit-identical to what the
+    reference computes on the same numpy/LAPACK.
+
+    The Butcher rows 1..n-2 solve, for k = 0..n-3 and every column j,
+        sum_{i=1}^{n-2} w_i c_i^k a_ij = (w_j/(k+1)) (1 - c_j^(k+1)) - w_{n-1} w_j
+    (c = points on [0, 1]).  The reference assembles all columns into ONE
+    n(n-2)-square system (equation (k, j) -> row j + k n, unknown a_ij -> column
+    (i-1) + j (n-2)) and calls ``numpy.linalg.solve``; the same matrix is formed
+    here (a blocked LU of the single system and n small solves need not agree
+    in the last bit, and the conditioning amplifies any such difference)."""
+    leg = np.polynomial.legendre.Legendre
+    if method == LOBATTO:
+        poly = leg([0] * (n - 1) + [1])
+        x = np.append(np.insert(poly.deriv().roots(), 0, -1, axis=0), 1)
+        w = np.array([1 / (n * (n - 1) * (poly(v) ** 2)) for v in x])
+        last_row = w
+    else:
+        x = np.concatenate([leg([0] * (n - 2) + [1, 1]).roots(), np.array([0])])
+        lower = leg([0] * (n - 2) + [1])
+        w = np.array([2 / (n - 1) ** 2]
+                     + [(1 - v) / ((n - 1) ** 2 * (lower(v) ** 2)) for v in x[1:-1]])
+        w = np.concatenate([w, np.array([0])])
+        last_row = w / 2
+    c = 0.5 * x + 0.5
+    butcher = np.zeros((n, n))
+    butcher[-1, :] = last_row
+    m = n - 2
+    if m > 0:
+        M = np.zeros((n * m, n * m))
+        rhs = np.zeros(n * m)
+        for k in range(m):
+            coef = [w[i + 1] * c[i + 1] ** k for i in range(m)]
+            for j in range(n):
+                M[j + k * n, j * m:(j + 1) * m] = coef
+                rhs[j + k * n] = (w[j] / (k + 1)) * (1 - c[j] ** (k + 1)) - w[-1] * w[j]
+        butcher[1:-1, :] = np.linalg.solve(M, rhs).reshape(m, -1, order="F")
+    return {"points": x, "weights": w, "butcher": butcher}
+
+
 class Quadrature:
     """Tables for one quadrature scheme; orders are generated lazily.
 
@@ -137,13 +193,16 @@ class Quadrature:
     (the ``[1 | -I]`` difference block).
     """
 
-    def __init__(self, method=LOBATTO):
+    def __init__(self, method=LOBATTO, tables="reference"):
         if method == GAUSS:
             raise ValueError("gauss quadrature is unsupported "
                              "(pycollo/quadrature.py:34-35)")
         if method not in QUADRATURE_METHODS:
             raise ValueError(f"unknown quadrature method {method!r}")
+        if tables not in ("reference", "exact"):
+            raise ValueError("tables must be 'reference' or 'exact'")
         self.method = method
+        self.tables = tables
         self._cache = {}
 
     @classmethod
@@ -184,8 +243,11 @@ class Quadrature:
             except KeyError:            # order absent from an adopted table set:
                 tab = None              # generate it (only auxiliary operators ask)
         if tab is None:
-            tab = (self._lobatto(order) if self.method == LOBATTO
-                   else self._radau(order))
+            if self.tables == "reference":
+                tab = _reference_numerics(order, self.method)
+            else:
+                tab = (self._lobatto(order) if self.method == LOBATTO
+                       else self._radau(order))
             self._cache[order] = tab
         return tab
 

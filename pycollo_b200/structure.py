@@ -32,17 +32,22 @@ import os
 
 import numpy as np
 
-# recipe word bit layout (must match csrc/pcx_kernels.cuh)
-RC_E_BITS, RC_B_BITS, RC_M_BITS, RC_C_BITS = 9, 9, 4, 7
+# recipe word bit layout (must match csrc/pcx_params.h).  Low word: staged row
+# (9 bits), quadrature-table index (13), constant index (7), three flags; high
+# word: variable (8), slot inside the variable's period (18), node inside the
+# section (5 bits: sections of up to 20 nodes, Settings.collocation_points_max).
+RC_E_BITS, RC_B_BITS, RC_M_BITS, RC_C_BITS = 9, 13, 5, 7
 RC_E_SHIFT = 0
 RC_B_SHIFT = RC_E_SHIFT + RC_E_BITS
-RC_M_SHIFT = RC_B_SHIFT + RC_B_BITS
-RC_C_SHIFT = RC_M_SHIFT + RC_M_BITS
+RC_C_SHIFT = RC_B_SHIFT + RC_B_BITS           # 22
 RC_PREV_BIT = RC_C_SHIFT + RC_C_BITS          # 29
 RC_PLAIN_BIT = RC_PREV_BIT + 1                # 30
 RC_SKIP_BIT = RC_PLAIN_BIT + 1                # 31
 RC_VAR_SHIFT = 32                             # variable index (8 bits)
 RC_LOCAL_SHIFT = 40                           # slot inside the variable's period
+RC_LOCAL_BITS = 18
+RC_M_SHIFT = RC_LOCAL_SHIFT + RC_LOCAL_BITS   # 58
+MAX_SECTION_NODES = 20
 
 # CTAs the kernels are compiled to keep resident per SM on large meshes
 RESIDENT_CTAS = 6
@@ -242,7 +247,7 @@ class NLPStructure:
         self.orders = orders
         if len(self.btab) >= (1 << RC_B_BITS):
             raise ValueError("too many distinct section orders for the recipe "
-                             "word (quadrature table exceeds 512 entries)")
+                             f"word (quadrature table exceeds {1 << RC_B_BITS} entries)")
         omax = max(orders)
         self.order_a_off = np.zeros(omax + 1, dtype=np.int32)
         self.order_w_off = np.zeros(omax + 1, dtype=np.int32)
@@ -378,6 +383,8 @@ class NLPStructure:
                         for (mloc, rk, idx, l, prev, st, bidx, cidx, plain,
                              skip) in rec[a]:
                             local = len(words) - offs[-1]
+                            if local >= (1 << RC_LOCAL_BITS) or mloc >= (1 << RC_M_BITS):
+                                raise ValueError("section too large for the recipe word")
                             words.append(
                                 (st << RC_E_SHIFT) | (bidx << RC_B_SHIFT)
                                 | (mloc << RC_M_SHIFT) | (cidx << RC_C_SHIFT)

@@ -13,6 +13,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A plain ``pytest`` run on a machine without a GPU skips the ``gpu`` tests
+    (so the CPU suite can gate CI); ``-m gpu`` -- what the GPU box runs -- keeps
+    the hard failure of the ``cuda_device`` fixture: a selected GPU test never
+    passes or skips silently without a device."""
+    if "gpu" in (config.getoption("-m") or ""):
+        return
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (select with -m gpu on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def cuda_device():
     import torch

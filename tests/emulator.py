@@ -268,11 +268,11 @@ def emulate(low, tables, scal, x, lam=None, sigma=1.0, flags=F_G | F_H,
                     if lo >> st.RC_SKIP_BIT:
                         continue
                     a = (w >> 32) & 0xff
-                    local = w >> 40
+                    local = (w >> st.RC_LOCAL_SHIFT) & ((1 << st.RC_LOCAL_BITS) - 1)
                     Pa = int(tv[a + 1] - tv[a])
                     e = lo & ((1 << st.RC_E_BITS) - 1)
                     bi = (lo >> st.RC_B_SHIFT) & ((1 << st.RC_B_BITS) - 1)
-                    mloc = (lo >> st.RC_M_SHIFT) & ((1 << st.RC_M_BITS) - 1)
+                    mloc = (w >> st.RC_M_SHIFT) & ((1 << st.RC_M_BITS) - 1)
                     ci = (lo >> st.RC_C_SHIFT) & ((1 << st.RC_C_BITS) - 1)
                     prev = (lo >> st.RC_PREV_BIT) & 1
                     plain = (lo >> st.RC_PLAIN_BIT) & 1

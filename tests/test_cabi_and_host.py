@@ -9,7 +9,8 @@ import pytest
 import sympy as sym
 
 import pycollo_b200
-from pycollo_b200 import OptimalControlProblem, examples
+from pycollo_b200 import OptimalControlProblem
+from examples import problems as examples
 from pycollo_b200 import engine as E
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -35,6 +36,10 @@ def test_no_cpu_fallback_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
     ocp = examples.brachistochrone()
+    with pytest.raises(E.PcxError, match="no CPU fallback"):
+        ocp.initialise()                      # compiles the engine: needs the device
+    ocp = examples.brachistochrone()
+    ocp.settings.defer_engine = True          # structure-only use stops before the device
     ocp.initialise()
     with pytest.raises(E.PcxError, match="no CPU fallback"):
         ocp._backend.evaluate_J(np.zeros(125))
@@ -88,6 +93,7 @@ def test_phase_symbols_and_errors():
 def test_initialise_layout_and_scaling_against_golden():
     g = np.load(os.path.join(ROOT, "tests", "golden", "iteration_scaling_double_pendulum.npz"))
     ocp = examples.double_pendulum()
+    ocp.settings.defer_engine = True
     ocp.initialise()
     it = ocp._backend.mesh_iterations[0]
     assert (it.num_x, it.num_c) == (190, 121)
@@ -126,6 +132,7 @@ def test_undefined_symbol_is_reported():
 def test_nlp_callback_orderings_are_permutations():
     from pycollo_b200.nlp import NlpCallbacks
     ocp = examples.cart_pole_swing_up()
+    ocp.settings.defer_engine = True
     ocp.initialise()
     it = ocp._backend.mesh_iterations[0]
     cb = NlpCallbacks(it)

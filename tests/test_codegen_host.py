@@ -15,7 +15,7 @@ import pytest
 import sympy as sym
 
 from helpers import build_case
-from pycollo_b200 import examples
+from examples import problems as examples
 
 HARNESS = r"""
 #include <cmath>

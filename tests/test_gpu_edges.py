@@ -5,7 +5,7 @@ import pytest
 
 from helpers import build_case, make_engine, max_err
 from pycollo_b200 import engine as E
-from pycollo_b200 import examples
+from examples import problems as examples
 
 pytestmark = pytest.mark.gpu
 ALL = E.EVAL_C | E.EVAL_DY | E.EVAL_JAC | E.EVAL_HESS | E.EVAL_F | E.EVAL_GRAD

@@ -10,7 +10,7 @@ import pytest
 
 from helpers import (RAGGED_NODES, RAGGED_SIZES, build_case, make_engine, max_err)
 from pycollo_b200 import engine as E
-from pycollo_b200 import examples
+from examples import problems as examples
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-12

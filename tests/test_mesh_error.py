@@ -12,7 +12,7 @@ import scipy.sparse as sp
 
 from helpers import GOLDEN
 from oracle import mesh_error as OM
-from pycollo_b200 import examples
+from examples import problems as examples
 from pycollo_b200.mesh import Mesh, PhaseMesh
 from pycollo_b200.quadrature import Quadrature
 

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from helpers import GOLDEN, golden_mesh
-from pycollo_b200 import examples
+from examples import problems as examples
 from pycollo_b200.symbolic import build_ir
 
 

@@ -17,7 +17,7 @@ import torch.multiprocessing as mp
 
 from helpers import build_case, max_err
 from pycollo_b200 import engine as E
-from pycollo_b200 import examples
+from examples import problems as examples
 from pycollo_b200.parallel import shard_range
 
 KEYS = ("c", "dy", "jac", "hess", "grad")

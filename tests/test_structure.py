@@ -8,7 +8,7 @@ import pytest
 from emulator import emulate
 from helpers import RAGGED_NODES, RAGGED_SIZES, build_case, max_err
 from pycollo_b200 import engine as E
-from pycollo_b200 import examples
+from examples import problems as examples
 
 CASES = [
     ("brachistochrone", 10, 4, None, {}),

@@ -5,7 +5,7 @@ import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
-from pycollo_b200 import examples
+from examples import problems as examples
 from pycollo_b200.backend import Cuda
 from pycollo_b200.nlp import NlpCallbacks
 

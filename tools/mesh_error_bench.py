@@ -7,7 +7,8 @@ import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
-from pycollo_b200 import engine as E, examples
+from pycollo_b200 import engine as E
+from examples import problems as examples
 from pycollo_b200.backend import lower_problem
 from pycollo_b200.mesh import Mesh, PhaseMesh
 from pycollo_b200.mesh_refinement import MeshErrorEvaluator, create_ph_mesh

@@ -6,7 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from helpers import build_case, make_engine
-from pycollo_b200 import engine as E, examples
+from pycollo_b200 import engine as E
+from examples import problems as examples
 from pycollo_b200.parallel import shard_range
 
 ALL = E.EVAL_C | E.EVAL_DY | E.EVAL_JAC | E.EVAL_HESS | E.EVAL_F | E.EVAL_GRAD

@@ -11,7 +11,8 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 import torch.distributed as dist
 from helpers import build_case
-from pycollo_b200 import engine as E, examples
+from pycollo_b200 import engine as E
+from examples import problems as examples
 from pycollo_b200.parallel import MeshSharder
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 83333          # x3 nodes x4 phases ~ 10^6 nodes

@@ -4,7 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from helpers import build_case
-from pycollo_b200 import engine as E, examples
+from pycollo_b200 import engine as E
+from examples import problems as examples
 os.environ["PCX_NVRTC_EXTRA"] = "-DPCX_DEBUG_TIMELINE"
 threads, tps, mb = (int(sys.argv[1]), int(sys.argv[2]) or None, int(sys.argv[3]) or None) if len(sys.argv) > 3 else (128, None, 6)
 low, _, scal = build_case(examples.cart_pole_swing_up(), "lobatto", 33333, 4, seed=0, unit_scaling=True,

@@ -4,7 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from helpers import build_case
-from pycollo_b200 import engine as E, examples
+from pycollo_b200 import engine as E
+from examples import problems as examples
 
 problem = sys.argv[1] if len(sys.argv) > 1 else "delta_iii_launch_vehicle"
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 83333
