@@ -8,7 +8,7 @@ What is produced
 ----------------
 ``quadrature_{lobatto,radau}.npz``
     points / weights / Butcher array / integration block ("A_matrix") for
-    every order 2..10, by *executing* ``pycollo/quadrature.py`` (loaded by file
+    every order 2..20, by *executing* ``pycollo/quadrature.py`` (loaded by file
     path with a tiny ``pyproprop`` shim, see ``oracle/refshim``).
 ``mesh_*.npz``
     ``Mesh.generate_single_phase`` outputs (tau, h_K, N_K, boundaries, W,
@@ -63,7 +63,7 @@ def dump_quadrature(quad_mod, method):
     backend = make_backend(quad_mod, method)
     q = backend.quadrature
     out = {}
-    for order in range(2, 11):
+    for order in range(2, 21):                      # Settings allow 2..20 (settings.py:234-251)
         out[f"points_{order}"] = np.asarray(q.quadrature_point(order), dtype=float)
         out[f"weights_{order}"] = np.asarray(q.quadrature_weight(order), dtype=float)
         out[f"butcher_{order}"] = np.asarray(q.butcher_array(order), dtype=float)

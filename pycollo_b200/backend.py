@@ -125,6 +125,17 @@ class Guess:
                         len(backend.ocp.parameter_variables))
         self.s = s[ir.s_needed] if len(s) else s
 
+    def _numeric(self, expr):
+        """A symbolic guess entry resolved through the auxiliary data and evaluated
+        in double precision operation by operation, as the reference's
+        ``expr_as_numeric`` does (``pycollo/backend.py:1382-1384``, CasADi ``DM``) --
+        not exactly-then-rounded, which can differ in the last bit."""
+        import sympy as sym
+        resolved = self._resolver(expr)
+        if resolved.free_symbols:
+            raise ValueError(f"guess entry '{expr}' does not resolve to a number")
+        return float(sym.lambdify([], resolved, modules="math")())
+
     def _check(self, guess, num_var, num_t=None):
         """Shape check + numeric resolution of symbolic guesses through the
         auxiliary data (``pycollo/guess.py:180-200``)."""
@@ -134,8 +145,7 @@ class Guess:
             return np.empty((0, num_t)) if num_t is not None else np.empty((0,))
         raw = np.asarray(guess, dtype=object)
         flat = np.array([v if isinstance(v, (int, float, np.floating, np.integer))
-                         else float(self._resolver(v)) for v in raw.ravel()],
-                        dtype=np.float64)
+                         else self._numeric(v) for v in raw.ravel()], dtype=np.float64)
         guess = flat.reshape(raw.shape)
         if num_t is not None:
             if guess.shape != (num_var, num_t):

@@ -36,6 +36,11 @@
 #ifndef PCX_MIN_BLOCKS
 #define PCX_MIN_BLOCKS 1
 #endif
+#ifndef PCX_SCATTER_UNROLL
+#define PCX_SCATTER_UNROLL 4
+#endif
+#define PCX_STR2(x) #x
+#define PCX_STR(x) PCX_STR2(x)
 
 // Small per-problem tables live in constant memory (set by the host after the
 // module is loaded and on every pcx_set_scaling): scaling products, slot bases.
@@ -225,7 +230,7 @@ __device__ __forceinline__ bool pcx_decode_slot(const PcxParams& p, const int ru
 __device__ __forceinline__ void pcx_store_run(double* o, const int ostep, const double* dp,
                                               const int dstep, const double bcoef,
                                               const double cc, const int cnt) {
-#pragma unroll 4
+    _Pragma(PCX_STR(unroll PCX_SCATTER_UNROLL))
     for (int it = 0; it < cnt; ++it) {
         *o = bcoef * (*dp) + cc;
         o += ostep; dp += dstep;

@@ -163,6 +163,9 @@ class NLPStructure:
         self._scales_setup()
         self._build_G()
         self._build_H()
+        # experiment knob (tools/knobs.py): tiles per SM on large meshes
+        if tiles_per_sm is None and os.environ.get("PCX_TILES_PER_SM"):
+            tiles_per_sm = int(os.environ["PCX_TILES_PER_SM"])
         self._build_tiles(sm_count, max_tile_nodes, smem_budget, tiles_per_sm)
         self._build_border()
 

@@ -161,10 +161,42 @@ def test_cyipopt_adapter_orderings_and_staging():
         # fused / single-output variants are separate compilations: rounding only
         assert max_err(cb.hessian(x, lam, 0.3), h_ccs[cb.h_perm]) <= 1e-13
         assert max_err(cc.hessian(x, lam, 0.3), h_ccs) <= 1e-13
+    # iterate cache: the five callbacks of one solver iterate ship x once and launch
+    # three kernels (f+grad+c fused, Jacobian, Hessian)
+    x = it.guess_x_tilde + 0.05
+    lam = rng.standard_normal(it.num_c)
+    up0, l0 = cb.num_x_uploads, dict(cb.num_launches)
+    f = cb.objective(x)
+    g = cb.gradient(x).copy()
+    c = cb.constraints(x).copy()
+    jac = cb.jacobian(x).copy()
+    hes = cb.hessian(x, lam, 1.0).copy()
+    assert cb.num_x_uploads == up0 + 1
+    assert [cb.num_launches[k] - l0[k] for k in ("point", "jacobian", "hessian")] == [1, 1, 1]
+    cb.objective(x); cb.jacobian(x)                                # same iterate again: cached
+    assert cb.num_x_uploads == up0 + 1 and cb.num_launches["jacobian"] == l0["jacobian"] + 1
+    assert f == backend.evaluate_J(x)
+    assert np.array_equal(g, backend.evaluate_g(x)) and np.array_equal(c, backend.evaluate_c(x))
+    assert np.array_equal(jac, backend.evaluate_G_nonzeros(x)[cb.g_perm])
+    assert max_err(hes, backend.evaluate_H_nonzeros(x, 1.0, lam)) <= 1e-13
+    x2 = x.copy(); x2[-1] += 1e-9                                  # one entry differs: new iterate
+    assert cb.objective(x2) == backend.evaluate_J(x2) and cb.num_x_uploads == up0 + 2
+    cs = NlpCallbacks(it, "cyipopt", x_check="sampled")
+    assert np.array_equal(cs.jacobian(x), jac) and cs.objective(x, new_x=False) == f
     rows, cols = cb.jacobianstructure()
     assert np.all(np.diff(rows) >= 0)                              # row-major
     hr, hc = cb.hessianstructure()
     assert np.all(hr >= hc)                                        # lower triangle
+    # derivative_level = 1: no Hessian is generated, compiled or exposed
+    ocp1 = examples.double_pendulum()
+    ocp1.settings.derivative_level = 1
+    ocp1.initialise()
+    cb1 = ocp1._backend.nlp_callbacks()
+    assert not hasattr(cb1, "hessian") and not hasattr(cb1, "hessianstructure")
+    x1 = ocp1._backend.mesh_iterations[0].guess_x_tilde
+    assert cb1.jacobian(x1).shape == (ocp1._backend.evaluate_G_num_nonzero(),)
+    with pytest.raises(ValueError, match="derivative_level"):
+        ocp1._backend.evaluate_H_nonzeros(x1, 1.0, None)
 
 
 @pytest.mark.parametrize("name,K,nodes,kw", [

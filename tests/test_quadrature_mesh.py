@@ -1,11 +1,14 @@
 """Host mesh/quadrature tables vs the reference's own (golden fixtures).
 
 Fixtures in tests/golden/ were produced by executing pycollo/quadrature.py and
-pycollo/mesh.py (oracle/make_golden.py).  The reference computes its Butcher
-arrays by an ill-conditioned linear solve (quadrature.py:141-163, 214-246) and
-loses digits at high order; the tables here are the exact collocation integrals,
-so the agreement bound grows with the order (checked against 50-digit arithmetic
-in DESIGN.md).  At the default order 4 the tables agree to 2e-15.
+pycollo/mesh.py (oracle/make_golden.py), orders 2..20.  The default tables
+(``Quadrature(method)``, ``tables="reference"``) reproduce the reference's
+numerics -- numpy's Legendre roots, the closed-form weights and the
+``numpy.linalg.solve`` of its simplifying-condition system -- and must equal the
+fixtures TO THE LAST BIT, including the digits that ill-conditioned solve loses at
+high order.  ``tables="exact"`` (collocation integrals by Gauss quadrature) is the
+mathematically exact alternative; its distance from the reference grows with the
+order and is bounded here.
 """
 import numpy as np
 import pytest
@@ -19,15 +22,26 @@ TOL_A = {2: 1e-15, 3: 1e-15, 4: 2e-15, 5: 4e-15, 6: 6e-15, 7: 2e-14, 8: 2e-13, 9
 
 
 @pytest.mark.parametrize("method", ["lobatto", "radau"])
-def test_tables_match_reference(method):
+def test_default_tables_are_the_references_bit_for_bit(method):
     g = np.load(f"{GOLDEN}/quadrature_{method}.npz")
     q = Quadrature(method)
+    for n in range(2, 21):
+        np.testing.assert_array_equal(q.quadrature_point(n), g[f"points_{n}"])
+        np.testing.assert_array_equal(q.quadrature_weight(n), g[f"weights_{n}"])
+        np.testing.assert_array_equal(q.butcher_array(n), g[f"butcher_{n}"])
+        np.testing.assert_array_equal(q.A_matrix(n), g[f"A_{n}"])
+        np.testing.assert_array_equal(q.D_matrix(n), g[f"D_{n}"])
+        assert q.A_matrix(n).shape == (n - 1, n)
+
+
+@pytest.mark.parametrize("method", ["lobatto", "radau"])
+def test_exact_tables_close_to_reference(method):
+    g = np.load(f"{GOLDEN}/quadrature_{method}.npz")
+    q = Quadrature(method, tables="exact")
     for n in range(2, 11):
         np.testing.assert_allclose(q.quadrature_point(n), g[f"points_{n}"], atol=4e-15, rtol=0)
         np.testing.assert_allclose(q.quadrature_weight(n), g[f"weights_{n}"], atol=1e-13, rtol=0)
         np.testing.assert_allclose(q.A_matrix(n), g[f"A_{n}"], atol=TOL_A[n], rtol=0)
-        np.testing.assert_array_equal(q.D_matrix(n), g[f"D_{n}"])
-        assert q.A_matrix(n).shape == (n - 1, n)
 
 
 def test_lobatto_weights_exact_low_order():
@@ -63,12 +77,12 @@ def test_mesh_matches_reference(method, tag):
     q = Quadrature(method)
     m = PhaseMeshData(q, PhaseMesh(len(g["N_K"]), g["sizes"], g["N_K"]), 2, 10)
     assert m.N == g["N"]
-    np.testing.assert_allclose(m.tau, g["tau"], atol=4e-15, rtol=0)
-    np.testing.assert_allclose(m.h_K, g["h_K"], atol=4e-15, rtol=0)
-    np.testing.assert_allclose(m.W_matrix, g["W"], atol=1e-13, rtol=0)
+    np.testing.assert_array_equal(m.tau, g["tau"])             # bit for bit
+    np.testing.assert_array_equal(m.h_K, g["h_K"])
+    np.testing.assert_array_equal(m.W_matrix, g["W"])
     sI, sA = m.sI_matrix, m.sA_matrix
     assert np.array_equal(sI.indptr, g["sI"].indptr) and np.array_equal(sI.indices, g["sI"].indices)
-    np.testing.assert_allclose(sI.data, g["sI"].data, atol=3e-12, rtol=0)
+    np.testing.assert_array_equal(sI.data, g["sI"].data)
     assert (sA != g["sA"]).nnz == 0
 
 

@@ -186,7 +186,7 @@ def test_gpu_fused_peer_exchange_same_device():
     for r, eng in enumerate(engines):
         eng.exchange_attach_ptr(r, world, 0, base)
     z = lambda n: torch.zeros(n, dtype=torch.float64, device="cuda")
-    for trial in range(3):                                   # epochs pair the calls
+    for trial in range(6):                                   # epochs pair the calls
         xn, ln = rng.uniform(-0.5, 0.5, S.num_x), rng.standard_normal(S.num_c)
         x, lam = torch.from_numpy(xn).cuda(), torch.from_numpy(ln).cuda()
         sig = torch.tensor([0.7], dtype=torch.float64, device="cuda")
@@ -199,3 +199,21 @@ def test_gpu_fused_peer_exchange_same_device():
         assert max_err(out["c"].cpu().numpy(), B.c(xn)) <= 1e-12
         assert max_err(out["grad"].cpu().numpy(), B.g(xn)) <= 1e-12
         assert max_err(out["f"].cpu().numpy(), [B.J(xn)]) <= 1e-12
+
+
+@pytest.mark.gpu
+def test_gpu_fused_exchange_across_processes():
+    """The cross-process path (CUDA IPC + st.release.sys / ld.acquire.sys + slot
+    back-pressure): two processes, one GPU each, 40 evaluations enqueued without
+    host synchronisation while the border rank starts late.  Needs 2 GPUs."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    script = os.path.join(os.path.dirname(__file__), "dist_fused_exchange.py")
+    res = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+         "--master-addr", "127.0.0.1", "--master-port", "29533", script],
+        capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "fused exchange across 2 processes" in res.stdout

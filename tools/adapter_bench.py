@@ -1,34 +1,43 @@
-"""cyipopt-style callback adapter (pycollo_b200/nlp.py) at BASELINE config 2:
-jacobian(x) + hessian(x, lam, sigma) per "iteration", host numpy in / host numpy
-out, row-major / lower-triangular ordering -- what an IPOPT host pays per iterate."""
+"""cyipopt-style callback adapter (pycollo_b200/nlp.py) at BASELINE config 2: the
+five callbacks of one solver iterate -- objective, gradient, constraints, jacobian,
+hessian at a NEW x -- host numpy in / host numpy out, row-major / lower-triangular
+ordering: what an IPOPT host pays per iterate.  Variants: how the object decides
+that x is unchanged (exact compare, sampled compare, the new_x flag of IPOPT's TNLP
+interface)."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np
 from examples import problems as examples
-from pycollo_b200.backend import Cuda
 from pycollo_b200.nlp import NlpCallbacks
 
 ocp = examples.cart_pole_swing_up()
 ocp.settings.scaling_method = "none"
 examples.set_mesh(ocp, 33333, 4)
-backend = Cuda(ocp)
-for step in ("create_bounds", "create_scaling", "create_quadrature",
-             "create_initial_mesh", "create_guess", "create_mesh_iterations"):
-    getattr(backend, step)()
-it = backend.current_iteration
-it.generate_nlp()
+ocp.initialise()
+it = ocp._backend.current_iteration
 rng = np.random.default_rng(0)
-x = rng.uniform(-0.5, 0.5, it.num_x)
+xs = [rng.uniform(-0.5, 0.5, it.num_x) for _ in range(4)]
 lam = rng.standard_normal(it.num_c)
-for ordering in ("cyipopt", "casadi"):
-    cb = NlpCallbacks(it, ordering)
-    for _ in range(3):
-        cb.jacobian(x); cb.hessian(x, lam, 1.0)
+
+
+def iterate(cb, x, flag):
+    kw = (lambda first: {}) if flag is None else (lambda first: dict(new_x=first))
+    cb.objective(x, **kw(True)); cb.gradient(x, **kw(False)); cb.constraints(x, **kw(False))
+    cb.jacobian(x, **kw(False)); cb.hessian(x, lam, 1.0, **kw(False))
+
+
+for ordering, x_check, flag in (("cyipopt", "full", None), ("cyipopt", "sampled", None),
+                                ("cyipopt", "full", True), ("casadi", "full", True)):
+    cb = NlpCallbacks(it, ordering, x_check)
+    for k in range(3):
+        iterate(cb, xs[k % 4], flag)
     n = 30
     t0 = time.perf_counter()
-    for _ in range(n):
-        cb.jacobian(x); cb.hessian(x, lam, 1.0)
+    for k in range(n):
+        iterate(cb, xs[k % 4], flag)
     dt = (time.perf_counter() - t0) / n
-    print(json.dumps(dict(adapter="NlpCallbacks", ordering=ordering, nodes=100000,
-                          ms_per_jac_plus_hess=round(1e3 * dt, 3), evals_per_s=round(1 / dt, 1))), flush=True)
+    print(json.dumps(dict(adapter="NlpCallbacks", ordering=ordering,
+                          same_x_test=("new_x flag" if flag else x_check), nodes=100000,
+                          callbacks_per_iterate=5, x_uploads_per_iterate=cb.num_x_uploads / (n + 3),
+                          ms_per_iterate=round(1e3 * dt, 3), iterates_per_s=round(1 / dt, 1))), flush=True)
