@@ -85,7 +85,7 @@ class Settings:
         self.default_mesh_section_sizes = None
         self.bound_clash_absolute_tolerance = 1e-6
         self.bound_clash_relative_tolerance = 1e-6
-        self.numerical_inf = 1e19
+        self.numerical_inf = 10e19       # sic: 1e20, pycollo/bounds.py:35 (its docstring says 1e19)
         self.override_endpoint_bounds = True
         self.remove_constant_variables = True
         self.console_out_progress = False
