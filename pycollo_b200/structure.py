@@ -52,6 +52,7 @@ MAX_SECTION_NODES = 20
 # CTAs the kernels are compiled to keep resident per SM on large meshes
 RESIDENT_CTAS = 6
 LARGE_MESH_THREADS = 128
+SMALL_BODY_THREADS = 192
 
 
 def resident_ctas(threads):
@@ -152,8 +153,16 @@ class NLPStructure:
             # CTA size: one thread per node of a tile; small problems (multi-start
             # sweeps of ~31-node meshes) get a CTA no wider than their mesh
             nmax = max(int(m.N) for m in meshes)
+            # large meshes: 128 threads x 6 CTAs/SM; small expression bodies (the
+            # ones the kernel parks in registers, <= 40 results per node: cart-pole)
+            # run 4 % faster with 192 x 4 -- fewer, fatter tiles amortise the
+            # per-tile prologue -- while larger bodies (robot, Delta III) lose
+            # 4-11 % there (measured, tools/knobs.py / tools/threads_ab.sh)
+            nout = max(pd.NF + len(pd.d1v) + len(pd.d1s) + len(pd.h2vv) + len(pd.h2vs)
+                       + len(pd.h2ss) + len(pd.htv) + len(pd.hts) for pd in phase_derivs)
+            large = SMALL_BODY_THREADS if nout <= 40 else LARGE_MESH_THREADS
             threads = 32 if nmax <= 32 else (64 if nmax <= 64 else
-                                             int(os.environ.get("PCX_THREADS", LARGE_MESH_THREADS)))
+                                             int(os.environ.get("PCX_THREADS", large)))
         self.threads = int(threads)
         self.P = len(ir.phases)
         self.NS = ir.n_s

@@ -54,7 +54,7 @@ def make_engine(low, scal, batch=1):
     return eng
 
 
-def max_err(a, b, b_err=None):
+def strict_err(a, b, b_err=None):
     """Worst deviation of ``a`` from the reference values ``b`` in units where
     ``<= 1e-12`` means exactly north_star's bar, element by element:
     ``|a-b| <= 1e-12*|b|``  OR  ``|a-b| <= 1e-14``.
@@ -79,11 +79,13 @@ def max_err(a, b, b_err=None):
     return float(np.max(units))
 
 
-def max_err_scaled(a, b):
-    """Scale-aware variant for vectors WITHOUT an exact reference (CUDA against
-    the fp64 oracle at 10^5-10^6 nodes, Delta-III-sized magnitudes): relative error
-    where the value is significant, absolute in units of 1 % of the vector's own
-    scale where cancellation leaves only the rounding noise of BOTH fp64 sides."""
+def max_err(a, b):
+    """Comparison of two fp64 IMPLEMENTATIONS (CUDA against the numpy oracle, sharded
+    against unsharded ...), where neither side is exact and both carry the rounding
+    noise of their own operation order: relative error where the value is
+    significant, absolute in units of 1 % of the vector's own scale where
+    cancellation leaves only that noise.  The strict north_star bar (``strict_err``)
+    is applied where an exactly rounded reference exists: the golden files."""
     a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
     assert a.shape == b.shape, (a.shape, b.shape)
     if a.size == 0:

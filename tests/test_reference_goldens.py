@@ -8,7 +8,7 @@ expansion ``iteration.py:86-194, 396-453``) on the same user scripts
 
 * sparsity indices: bit-exact (G in CCS order, H upper triangle in CCS order);
 * values: ``|a-b| <= 1e-12*|b|`` or ``<= 1e-14`` element by element
-  (``helpers.max_err``; an element whose own fp64 evaluation by the reference is
+  (``helpers.strict_err``; an element whose own fp64 evaluation by the reference is
   ill-conditioned is held to 4x the reference's running-error bound instead),
   observed maxima printed;
 * CPU tests pin the oracle and the host-side mirror (mesh tables bit for bit,
@@ -21,7 +21,7 @@ import numpy as np
 import pytest
 
 from examples.cases import GOLDEN_CASES, build_golden_problem
-from helpers import GOLDEN, max_err
+from helpers import GOLDEN, strict_err
 from pycollo_b200.backend import lower_problem
 from pycollo_b200.mesh import PhaseMeshData
 from pycollo_b200.quadrature import Quadrature
@@ -111,7 +111,7 @@ def _check_values(name, g, fns, label):
         got = fns(x, lam, sg)
         for key, val in got.items():
             ref = g[key][k]
-            e = max_err(np.reshape(val, np.shape(ref)), ref, g[key + "_err"][k])
+            e = strict_err(np.reshape(val, np.shape(ref)), ref, g[key + "_err"][k])
             worst[key] = max(worst.get(key, 0.0), e)
     print(f"{label} {name}: " + "  ".join(f"{k} {v:.1e}" for k, v in worst.items()))
     bad = {k: v for k, v in worst.items() if v > RTOL}
@@ -197,8 +197,8 @@ def test_cuda_backend_matches_reference(name, cuda_device):
     # N1: w and W from the device (scaling.py:346-430).  Delta III's guess is a
     # singular point of its dynamics (the reference's own G is not finite there)
     if not bool(g["singular_guess"]):
-        assert max_err([it.scaling.w], [float(g["w"])]) <= RTOL
-        e_W = max_err(it.scaling.W_ocp, g["W_ocp"])
+        assert strict_err([it.scaling.w], [float(g["w"])]) <= RTOL
+        e_W = strict_err(it.scaling.W_ocp, g["W_ocp"])
         print(f"cuda {name}: W_ocp {e_W:.1e}")
         assert e_W <= RTOL
     rows, cols = be.evaluate_G_structure()

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, first GPU contact: tests, bench at the driver's settings and defaults, knobs
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x --deselect tests/test_sharding.py::test_gpu_fused_exchange_across_processes > gpurun_out/r02a_gputests.log 2>&1
+python -m pytest tests -m gpu -q --deselect tests/test_sharding.py::test_gpu_fused_exchange_across_processes > gpurun_out/r02a_gputests.log 2>&1
 echo "pytest exit $?"; tail -5 gpurun_out/r02a_gputests.log
 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02a_bench_20.json 2> gpurun_out/r02a_bench_20.err
 echo "bench20 exit $?"; cat gpurun_out/r02a_bench_20.json | cut -c1-600
