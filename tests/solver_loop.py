@@ -126,7 +126,9 @@ def solve(cb, x0, x_lo, x_hi, c_lo, c_hi, tol=1e-8, max_iter=500, verbose=False)
     zu = np.where(has_hi, mu / np.where(has_hi, hi - v, 1.0), 0.0)
     lam = np.zeros(m)
     f, g, h, A = funcs(v)
-    nu, delta_last, it = 1.0, 0.0, 0
+    delta_last, it = 0.0, 0
+    filt, filt_mu = [], None
+    theta_init = float(np.sum(np.abs(h)))
     N = n + ns
     for it in range(1, max_iter + 1):
         dl = np.where(has_lo, v - lo, 1.0)
@@ -175,22 +177,30 @@ def solve(cb, x0, x_lo, x_hi, c_lo, c_hi, tol=1e-8, max_iter=500, verbose=False)
 
         a_p = min(max_step(dl, dv, has_lo), max_step(du, -dv, has_hi))
         a_d = min(max_step(zl, dzl, has_lo), max_step(zu, dzu, has_hi))
-        # l1 merit function on the barrier problem
+        # globalisation: IPOPT's filter acceptance test (its eq. 18-20) with the
+        # filter reset at every barrier update -- a trial point is taken if it
+        # improves the constraint violation or the barrier objective sufficiently
+        # and is not dominated by an earlier iterate of this barrier problem
         phi0 = barrier(v, f, mu)
+        theta0 = np.sum(np.abs(h))
         dphi = rhs_d @ dv - (A.T @ lam) @ dv
-        hn = np.sum(np.abs(h))
-        if hn > 0:
-            nu = max(nu, (dphi + 0.5 * max(curv, 0.0)) / (0.9 * hn))
-        d_merit = dphi - nu * hn
+        if mu != filt_mu:
+            filt, filt_mu = [], mu
         alpha = a_p
-        for ls in range(30):
+        for ls in range(40):
             v_new = v + alpha * dv
             f_n, g_n, h_n, A_n = funcs(v_new)
-            if np.isfinite(f_n) and np.all(np.isfinite(h_n)) and \
-               barrier(v_new, f_n, mu) + nu * np.sum(np.abs(h_n)) <= \
-               phi0 + nu * hn + 1e-8 * alpha * d_merit:
-                break
+            if np.isfinite(f_n) and np.all(np.isfinite(h_n)):
+                th, ph = np.sum(np.abs(h_n)), barrier(v_new, f_n, mu)
+                if theta0 <= 1e-4 * max(1.0, theta_init) and dphi < 0 and \
+                        alpha * (-dphi) ** 2.3 > theta0 ** 1.1:
+                    okay = ph <= phi0 + 1e-8 * alpha * dphi        # Armijo on the barrier
+                else:
+                    okay = th <= (1 - 1e-5) * theta0 or ph <= phi0 - 1e-5 * theta0
+                if okay and all(th < (1 - 1e-5) * t_ or ph < p_ - 1e-5 * t_ for t_, p_ in filt):
+                    break
             alpha *= 0.5
+        filt.append((theta0, phi0))
         v, f, g, h, A = v_new, f_n, g_n, h_n, A_n
         lam = lam + alpha * dlam
         zl = np.where(has_lo, zl + a_d * dzl, 0.0)

@@ -46,10 +46,12 @@ def test_single_section_orders(nodes):
 
 
 def test_cta_sizes_follow_the_mesh():
-    """32 / 64 / 128 threads per CTA for meshes of <= 32 / <= 64 / more nodes, and a
-    tile never holds more nodes than threads."""
-    for K, want in ((10, 32), (20, 64), (30, 128)):
-        low = _parity("cart_pole_swing_up", "lobatto", K, 4)
+    """32 / 64 threads per CTA for meshes of <= 32 / <= 64 nodes; larger meshes: 192
+    for small expression bodies (cart-pole), 128 for large ones (robot); a tile never
+    holds more nodes than threads."""
+    for name, K, want in (("cart_pole_swing_up", 10, 32), ("cart_pole_swing_up", 20, 64),
+                          ("cart_pole_swing_up", 30, 192), ("free_flying_robot", 30, 128)):
+        low = _parity(name, "lobatto", K, 4)
         assert low.S.threads == want and low.S.max_tile_nodes <= want
     # one tile per instance takes the single-CTA path (tile + border pass in one CTA)
     low = _parity("free_flying_robot", "lobatto", 10, 4)
