@@ -59,14 +59,18 @@ def main():
         sh.evaluate(what, x, lam=lam, sigma=sig, **o)
     torch.cuda.synchronize()
     assert eng.status() == 0, "exchange timed out"
-    worst = 0.0
-    for o, r in zip(out, ref):
+    worst, bad = 0.0, []
+    for i, (o, r) in enumerate(zip(out, ref)):
         for k in ("c", "jac", "hess", "grad", "f"):
             t = o[k].clone()
             dist.all_reduce(t)                          # sum of disjoint slabs (+ border rank's slots)
             d = float((t - r[k]).abs().max())
             s = float(r[k].abs().max()) or 1.0
             worst = max(worst, d / s)
+            if d / s > 1e-13:
+                bad.append((i, k, d / s, int((t - r[k]).abs().argmax())))
+    if rank == 0 and bad:
+        print("deviating (evaluation, output, rel. deviation, slot):", bad[:24], flush=True)
     assert worst <= 1e-13, worst
     if rank == 0:
         print(f"fused exchange across {world} processes: {n_evals} evaluations, "
