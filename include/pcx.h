@@ -185,7 +185,12 @@ int pcx_apply_border(pcx_engine* e, int what, const double* x, const double* lam
  *   rel_err[...] = abs / (1 + (max_l |Y| + 1))   (sic, :224, :229-234)
  *   max_rel[sec_off_p + k] = max over states and nodes            (:237-240)
  * with mmax_p = max_k N_k(ph) - 1 and zeros in the unused tail, phases
- * concatenated.  Any output may be NULL.                                     */
+ * concatenated.  Any output may be NULL.
+ * Multi-GPU: on an engine restricted to a tile
+ * range (pcx_set_shard) only the sections of that range are evaluated and only
+ * their entries of abs_err / rel_err / max_rel are written -- the pass is
+ * section-local, there is no exchange; a global maximum, if wanted, is one
+ * all_reduce(max) of max_rel over the ranks.                                  */
 int pcx_mesh_error(pcx_engine* e, const double* x_ph, double* abs_err,
                    double* rel_err, double* max_rel, int space, void* stream);
 /* lengths (per instance) of abs_err/rel_err and of max_rel                    */

@@ -37,19 +37,50 @@ class MeshErrorEvaluator:
     """One engine on the ph mesh of an iteration's mesh; reusable for any number
     of ``x_ph`` vectors (and ``batch`` of them per call)."""
 
-    def __init__(self, ocp, mesh, batch=1, device=0, collocation_points_max=21):
+    def __init__(self, ocp, mesh, batch=1, device=0, collocation_points_max=21,
+                 shard=None, **structure_kwargs):
+        """``shard=(rank, world_size)``: the error pass of one mesh split over the
+        ranks by contiguous section ranges -- it is
+        section-local, so there is no exchange; each rank fills the entries of its
+        sections (``local_sections``) and leaves the others untouched."""
         from .backend import lower_problem
+        from .parallel import shard_range
         self.ph_mesh = create_ph_mesh(mesh, 2, collocation_points_max)
-        self.low = lower_problem(ocp, self.ph_mesh.p)
+        self.low = lower_problem(ocp, self.ph_mesh.p, **structure_kwargs)
         S = self.low.S
         self.engine = _engine.Engine(S, self.low.layouts, self.low.header,
                                      batch=batch, device=device)
         # user basis: V = 1, r = 0, W = 1, w = 1 (mesh_refinement.py:149-150)
         self.engine.set_scaling(np.ones(S.n_var_ocp), np.zeros(S.n_var_ocp),
                                 np.ones(S.n_con_ocp), 1.0)
+        self.local_sections = [(0, int(t.K)) for t in S.ph]
+        if shard is not None:
+            rank, world = shard
+            lo, hi = shard_range(S.num_tiles, world, rank)
+            self.engine.set_shard(lo, hi)
+            secs = []
+            for ip in range(len(S.ph)):
+                sel = np.flatnonzero(S.tile_phase[lo:hi] == ip) + lo
+                secs.append((int(S.tile_k0[sel].min()), int(S.tile_k1[sel].max()))
+                            if len(sel) else (0, 0))
+            self.local_sections = secs
 
     def __call__(self, x_ph):
         return self.engine.mesh_error_host(x_ph)
+
+    def global_maximum(self, max_rel_per_phase):
+        """Largest relative error over the whole mesh: the local maximum of this
+        rank's sections, then one ``all_reduce(MAX)`` when a process group exists."""
+        import torch
+        import torch.distributed as dist
+        local = max([float(np.max(m[lo:hi])) for m, (lo, hi) in
+                     zip(max_rel_per_phase, self.local_sections) if hi > lo] + [0.0])
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dev = f"cuda:{self.engine.device}" if dist.get_backend() == "nccl" else "cpu"
+            t = torch.tensor([local], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            local = float(t[0])
+        return local
 
 
 class PattersonRaoMeshRefinement:

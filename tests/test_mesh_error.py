@@ -242,3 +242,79 @@ def test_gpu_refit_to_ph_matches_reference_fits(problem, method, nodes):
         off += (ny + nu) * Nph + nqt
     assert np.array_equal(x_ph[off:], x[S.s_off:])
     assert off + S.NS == eng.refit_size()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("problem,K,nodes", [("free_flying_robot", 40, 4),
+                                             ("multiphase_sliding_mass", 24, [3, 5, 4] * 8)])
+def test_gpu_mesh_error_sharded_by_section(problem, K, nodes):
+    """the error pass of one mesh split over three
+    "ranks" (three engines restricted to disjoint tile ranges on one device).  It is
+    section-local -- no exchange: every section is evaluated by exactly one rank,
+    the union of the ranks' entries is the unsharded result bit for bit, and the
+    global maximum is the maximum of the local maxima."""
+    from pycollo_b200.mesh import Mesh, PhaseMesh
+    from pycollo_b200.mesh_refinement import MeshErrorEvaluator
+    from pycollo_b200.quadrature import Quadrature
+    ocp = getattr(examples, problem)()
+    ocp.settings.scaling_method = "none"
+    mesh = Mesh(Quadrature("lobatto"), [PhaseMesh(K, None, nodes) for _ in ocp.phases], 2, 20)
+    whole = MeshErrorEvaluator(ocp, mesh, max_tile_nodes=24)
+    rng = np.random.default_rng(8)
+    x_ph = rng.uniform(0.1, 0.9, whole.low.S.num_x)
+    ref = whole(x_ph)
+    world = 3
+    parts = [MeshErrorEvaluator(ocp, mesh, shard=(r, world), max_tile_nodes=24) for r in range(world)]
+    assert whole.low.S.num_tiles >= world
+    got = [p(x_ph) for p in parts]
+    for ip, (a_ref, r_ref, m_ref) in enumerate(ref):
+        owner = np.zeros(len(m_ref), dtype=int)
+        a_sum, r_sum, m_sum = np.zeros_like(a_ref), np.zeros_like(r_ref), np.zeros_like(m_ref)
+        for p, res in zip(parts, got):
+            lo, hi = p.local_sections[ip]
+            owner[lo:hi] += 1
+            a, r, m = res[ip]
+            assert not a[:lo].any() and not a[hi:].any() and not m[:lo].any() and not m[hi:].any()
+            a_sum += a; r_sum += r; m_sum += m
+        assert np.all(owner == 1)                       # one rank per section
+        np.testing.assert_array_equal(a_sum, a_ref)
+        np.testing.assert_array_equal(r_sum, r_ref)
+        np.testing.assert_array_equal(m_sum, m_ref)
+    worst = max(p.global_maximum([res[ip][2] for ip in range(len(ref))]) for p, res in zip(parts, got))
+    assert worst == max(float(m.max()) for _, _, m in ref)
+
+
+SOLUTION_CASES = ["brachistochrone_lobatto", "brachistochrone_lobatto_ragged", "cart_pole_radau",
+                  "free_flying_robot_lobatto", "multiphase_lobatto", "hypersensitive_radau"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SOLUTION_CASES)
+def test_gpu_solution_chain_matches_executed_reference(name):
+    """Rows a11 / N2 / a12 against the reference ITSELF (``oracle/make_golden_solution.py``
+    executes the unmodified ``CasadiSolution`` -> ``interpolate_solution_*`` ->
+    ``PattersonRaoMeshRefinement`` chain on a synthetic iterate): state derivatives
+    (``PCX_EVAL_DY``), the solution re-fitted onto the p+1 mesh on the device
+    (``pcx_refit_to_ph``) and the mesh errors (``pcx_mesh_error``)."""
+    from examples.cases import build_golden_problem
+    from helpers import max_err, strict_err
+    from pycollo_b200.solution import Solution
+    g = np.load(f"{GOLDEN}/solution_{name}.npz")
+    ocp = build_golden_problem(name)
+    ocp.initialise()
+    it = ocp._backend.mesh_iterations[0]
+    sol = Solution(it, g["x"], J=None)
+    dy = np.concatenate([np.ravel(p.dy) for p in sol.phase_data])
+    e_dy = max_err(dy, g["dy"])
+    mr = sol.refine_mesh()
+    e_xph = max_err(mr.x_ph, g["x_ph"])
+    worst = 0.0
+    for ip in range(int(g["num_phases"])):
+        np.testing.assert_array_equal(mr.ph_mesh.tau[ip], g[f"tau_ph_{ip}"])
+        for ours, key in ((mr.absolute_mesh_errors[ip], "abs"), (mr.relative_mesh_errors[ip], "rel"),
+                          (mr.maximum_relative_mesh_errors[ip], "max")):
+            worst = max(worst, max_err(ours, g[f"{key}_{ip}"]))
+    print(f"solution chain {name}: dy {e_dy:.1e}  x_ph {e_xph:.1e}  mesh errors {worst:.1e}")
+    # the reference fits least-squares polynomials in a [0, 1] window (loses ~1e-13 at
+    # order 6); the device applies the exact interpolation matrices
+    assert e_dy <= 1e-12 and e_xph <= 1e-11 and worst <= 1e-9
