@@ -172,6 +172,8 @@ class NLPStructure:
         self._scales_setup()
         self._build_G()
         self._build_H()
+        if os.environ.get("PCX_SMEM_BUDGET"):            # experiment knob: bytes staged per tile
+            smem_budget = int(os.environ["PCX_SMEM_BUDGET"])
         # experiment knob (tools/knobs.py): tiles per SM on large meshes
         if tiles_per_sm is None and os.environ.get("PCX_TILES_PER_SM"):
             tiles_per_sm = int(os.environ["PCX_TILES_PER_SM"])

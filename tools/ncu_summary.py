@@ -9,6 +9,7 @@
 import csv, json, os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, rnd = sys.argv[1], sys.argv[2]
+name = sys.argv[3] if len(sys.argv) > 3 else "pcx_fill"      # e.g. "d3" for the Delta III capture
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 KEEP = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "dram__bytes_read.sum",
         "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -42,7 +43,7 @@ for n, j in stall:
             out.append([n, units[j]] + [d[j] for d in data])
     except ValueError:
         pass
-dst = os.path.join(P, f"r{rnd}_pcx_fill_ncu_full.csv")
+dst = os.path.join(P, f"r{rnd}_{name}_ncu_full.csv")
 with open(dst, "w") as fh:
     fh.write(f"# ncu --set full --clock-control none --import-source on -k regex:pcx_fill -s 8 -c 1 (tools/prof.sh {tag})\n")
     csv.writer(fh).writerows(out)
@@ -56,11 +57,37 @@ def tobytes(v, unit):
 jr, jw = names.index("dram__bytes_read.sum"), names.index("dram__bytes_write.sum")
 rd = sum(tobytes(d[jr], units[jr]) for d in data) / len(data)
 wr = sum(tobytes(d[jw], units[jw]) for d in data) / len(data)
-json.dump({"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
+steady = os.path.join(G, f"steady_{tag}.csv")
+if name != "pcx_fill":
+    pass
+elif os.path.exists(steady):
+    # steady state: N consecutive ring launches measured in their natural cache state
+    # (ncu --cache-control none, one pass: no replay), DRAM bytes averaged per launch
+    acc = {"dram__bytes_read.sum": [], "dram__bytes_write.sum": [], "gpu__time_duration.sum": []}
+    for r in csv.reader(open(steady)):
+        if len(r) > 14 and r[12] in acc:
+            acc[r[12]].append(float(r[14].replace(",", "")))
+    n = len(acc["dram__bytes_read.sum"])
+    srd, swr = sum(acc["dram__bytes_read.sum"]) / n, sum(acc["dram__bytes_write.sum"]) / n
+    json.dump({"dram_bytes_per_launch": srd + swr, "dram_read": srd, "dram_write": swr,
+               "launches_averaged": n,
+               "kernel_ns_median_serialised": sorted(acc["gpu__time_duration.sum"])[n // 2],
+               "cold_single_launch": {"dram_read": rd, "dram_write": wr},
+               "source": f"gpurun_out/steady_{tag}.csv: ncu --cache-control none --clock-control none "
+                         f"--metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:pcx_fill -s 12 -c {n} "
+                         f"on `bench.py --steps 40`: {n} consecutive launches of the ring of 6 buffer sets "
+                         f"(255 MB > L2), each in its natural cache state -- the write-back of earlier "
+                         f"launches' values is counted where it happens, so the average is the steady-state "
+                         f"DRAM traffic per evaluation.  cold_single_launch: the --set full capture (caches "
+                         f"flushed before one replayed launch; its values stay in L2 until later launches)"},
+              open(os.path.join(P, "traffic.json"), "w"), indent=1)
+    shutil.copy(steady, os.path.join(P, f"r{rnd}_steady_state_dram.csv"))
+else:
+    json.dump({"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
            "source": f"profiles/r{rnd}_pcx_fill_ncu_full.csv (ncu --set full, one replayed launch: most of the "
                      f"~39 MB of values written stay in the 126 MB L2 inside one launch and are evicted "
                      f"later, so the in-launch DRAM writes are far below the algorithmic bytes)"},
-          open(os.path.join(P, "traffic.json"), "w"), indent=1)
+              open(os.path.join(P, "traffic.json"), "w"), indent=1)
 # launch list
 src = os.path.join(G, f"launches_{tag}.csv")
 if os.path.exists(src):
@@ -86,7 +113,7 @@ if os.path.exists(src):
             fh.write(f"{k},{len(v)},{sum(v):.0f},{v[len(v)//2]:.0f},{v[0]:.0f},{v[-1]:.0f},{sum(v)/tot:.4f}\n")
 hot = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "srcprof.py"),
                       os.path.join(G, f"src_{tag}.csv"), "0.8"], capture_output=True, text=True).stdout
-open(os.path.join(P, f"r{rnd}_source_hotspots.txt"), "w").write(
+open(os.path.join(P, f"r{rnd}_source_hotspots.txt" if name == "pcx_fill" else f"r{rnd}_{name}_source_hotspots.txt"), "w").write(
     "# per source line of pcx_kernels.cuh / the generated pcx_problem.h: share of executed warp instructions,\n"
     "# share of stall samples, dominant stall reasons (ncu --page source --print-source cuda,sass)\n" + hot)
 print(open(dst).read()[:3000])
