@@ -39,10 +39,21 @@ def test_smallest_meshes(name, method):
         build_case(getattr(examples, name)(), method, 1, 2, oracle=False)
 
 
-@pytest.mark.parametrize("nodes", [3, 10, 16])
+@pytest.mark.parametrize("nodes", [3, 10, 16, 17, 20])
 def test_single_section_orders(nodes):
+    """Up to Settings.collocation_points_max = 20 nodes per section (the recipe word's
+    node field was 4 bits wide in round 1: sections of 17-20 nodes scattered wrong
+    Jacobian values silently)."""
     _parity("cart_pole_swing_up", "lobatto", 1, nodes)
     _parity("hypersensitive", "radau", 1, nodes)
+
+
+def test_sections_of_17_to_20_nodes_in_one_mesh():
+    _parity("brachistochrone", "lobatto", 4, [18, 17, 20, 19])
+    _parity("double_pendulum", "radau", 3, [20, 4, 18], max_tile_nodes=24)
+    # the ph mesh of a 20-node section has 21 nodes: the mesh-error engine's limit
+    with pytest.raises(ValueError):
+        _parity("hypersensitive", "lobatto", 1, 33)
 
 
 def test_cta_sizes_follow_the_mesh():

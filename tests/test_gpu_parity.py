@@ -152,13 +152,22 @@ def test_device_pointers_and_determinism(cuda_device):
         assert np.array_equal(jac.cpu().numpy(), j1) and np.array_equal(hes.cpu().numpy(), h1)
 
 
-def test_full_size_config2_properties(cuda_device):
-    """BASELINE config 2 (cart-pole, 10^5 nodes): oracle comparison at full size
-    plus size-independent properties (linearity of H in (sigma, lam))."""
+@pytest.mark.parametrize("method", ["lobatto", "radau"])
+def test_full_size_config2_properties(method, cuda_device):
+    """BASELINE config 2 (cart-pole, 10^5 nodes) under both schemes -- Radau is the
+    one the config names: oracle comparison at full size plus size-independent
+    properties (linearity of H in (sigma, lam)).  The patterns behind the counts are
+    pinned to the reference at N = 31 (tests/test_reference_goldens.py: cart_pole_lobatto
+    1172 / 155, cart_pole_radau 941 / 150 = the same per-section formulas)."""
     ocp = examples.cart_pole_swing_up()
-    low, B, scal = build_case(ocp, "lobatto", 33333, 4, seed=9)
+    low, B, scal = build_case(ocp, method, 33333, 4, seed=9)
     S = low.S
-    assert (S.num_x, S.num_c, S.nnz_g, S.nnz_h) == (500001, 399997, 3899963, 500000)
+    # Lobatto: 38(N-1) + N + 1 and 5N (SURVEY.md section 8(d)).  Radau: the exactly-zero
+    # last integration column / last weight of every section prune 23 Jacobian entries per
+    # section, and the phase's last node (zero weight everywhere) carries no Hessian block
+    want = (3899963, 500000) if method == "lobatto" else (3133303, 499995)
+    assert (S.num_x, S.num_c) == (500001, 399997)
+    assert (S.nnz_g, S.nnz_h) == want, (S.nnz_g, S.nnz_h)
     eng = make_engine(low, scal)
     rng = np.random.default_rng(0)
     x = rng.uniform(-0.5, 0.5, S.num_x)

@@ -1,6 +1,6 @@
 """Sparsity structure (bit-exact) and device tables (through the CPU emulation)
 against the oracle, on the edge cases the domain has: ragged meshes, sections of
-2..10 nodes, Radau zero pruning, free/fixed times, static parameters, tiles
+2..20 nodes, Radau zero pruning, free/fixed times, static parameters, tiles
 smaller than the mesh, random objective/constraint scaling."""
 import numpy as np
 import pytest
@@ -18,6 +18,10 @@ CASES = [
     ("free_flying_robot", 5, [4, 6, 3, 5, 4], None, dict(max_tile_nodes=12)),
     ("multiphase_sliding_mass", 4, 4, None, {}),
     ("space_shuttle_reentry", 4, [4, 3, 5, 4], None, dict(max_tile_nodes=10)),
+    # sections of 17-20 nodes (Settings.collocation_points_max = 20): the recipe word's
+    # node field is 5 bits wide since round 2
+    ("brachistochrone", 4, [18, 17, 20, 19], None, {}),
+    ("hypersensitive", 3, [20, 4, 18], [0.5, 0.2, 0.3], dict(max_tile_nodes=24)),
 ]
 
 
