@@ -33,7 +33,8 @@ One *step* = one evaluation of (G values, H values) for one synthetic iterate
 * ``--impl reference``: the reference's CPU implementation of this path.  The
   live reference (CasADi) cannot be installed here (no casadi/pyproprop wheel,
   no network), so this arm times the oracle port with every host
-  thread it can use (numba node kernel) and reports the 1-thread figure beside it.
+  thread it can use -- inside one evaluation (numba node kernel) and as one
+  independent stream per core; `value` is the better, the 1-thread figure beside it.
 
 Multi-GPU (``torchrun``): the headline is weak scaling, one independent
 multi-start instance of the same workload per rank, no data-path collective;
@@ -242,6 +243,13 @@ def cpu_baseline_block(single_budget=10.0):
 
 
 def run_reference(args):
+    """The reference arm: the CPU implementation of the path on the box's host cores,
+    with all the host threads it can use.  Two ways exist to use them with the
+    reference's single-threaded algorithm: inside one evaluation (node functions in a
+    numba.prange kernel; the sparse assembly stays serial) or one independent
+    evaluation stream per core (multi-start throughput).  Both are measured, each
+    step a bounded sample; `value` is the better of the two, the other figures and
+    the one-thread rate are reported beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -259,34 +267,41 @@ def run_reference(args):
     for i in range(max(1, min(warmup, 3))):
         B.G_nonzeros(xs[i % 2])
         B.H_nonzeros(xs[i % 2], 1.0, lams[i % 2])
-    steps = max(1, min(steps, 60))                  # bounded: ~0.1-0.25 s per eval
+    steps = max(1, min(steps, 60))                  # bounded: ~0.1 s per eval
     t0 = time.perf_counter()
     for i in range(steps):
         B.G_nonzeros(xs[i % 2])
         B.H_nonzeros(xs[i % 2], 1.0, lams[i % 2])
     dt = time.perf_counter() - t0
-    value = steps / dt
+    inside = steps / dt
+    extra = {"inside_one_evaluation": {"value": inside, "unit": UNIT, "cores": cores,
+                                       "how": f"node functions by {kind_eval} on {cores} thread(s), "
+                                              f"{steps} evaluations in {dt:.1f} s"}}
+    value, how, used = inside, f"{kind_eval} node kernel on {cores} thread(s) inside one evaluation", cores
+    try:
+        r1, n1, dt1 = cpu_oracle_rate("numpy", 8.0)
+        extra["single_thread"] = {"value": r1, "unit": UNIT, "cores": 1,
+                                  "sample": f"{n1} evaluations in {dt1:.1f} s"}
+        allc = cpu_oracle_rate_all_cores()
+        extra["all_cores"] = allc
+        if allc["value"] > value:
+            value, used = allc["value"], allc["cores"]
+            how = (f"{allc['cores']} independent single-threaded evaluation streams, one per "
+                   f"host core (the better of the two ways to use every core)")
+    except Exception as exc:
+        extra["all_cores"] = {"error": repr(exc)[:200]}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+            "ms_per_step": 1e3 / value, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{steps} fused G+H evaluations of the full "
-                                       f"10^5-node workload by oracle/blockwise.py, node "
-                                       f"functions evaluated by {kind_eval} on {cores} "
-                                       f"thread(s); the live reference (CasADi) is not "
-                                       f"installable here"},
+            "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": used, "kind": "port",
+                                  "sample": f"fused G+H evaluations of the full 10^5-node workload "
+                                            f"by oracle/blockwise.py: {how}; the live reference "
+                                            f"(CasADi) is not installable here"}, **extra),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    try:
-        r1, n1, dt1 = cpu_oracle_rate("numpy", 8.0)
-        line["cpu_baseline"]["single_thread"] = {"value": r1, "unit": UNIT, "cores": 1,
-                                                 "sample": f"{n1} evaluations in {dt1:.1f} s"}
-        line["cpu_baseline"]["all_cores"] = cpu_oracle_rate_all_cores()
-    except Exception as exc:
-        line["cpu_baseline"]["all_cores"] = {"error": repr(exc)[:200]}
     print(json.dumps(line))
     return 0
 
@@ -370,7 +385,10 @@ def strong_scaling(args, torch, dist, E, rank, world, local_rank):
         sh.evaluate(what, x, lam=lam, jac=jac[i % R], hess=hes[i % R])
     torch.cuda.synchronize()
     dist.barrier()
-    msN = eng.eval_many(what, cargs, steps, stream=st, gate=True, timed=True) / steps
+    # 6 untimed launches first, in the same call: their exchange brings the ranks into
+    # step, so the timed ones do not contain the ranks' start-up skew (which, over a
+    # ~2 ms timed region, would otherwise be charged to the border rank)
+    msN = eng.eval_many(what, cargs, steps, stream=st, gate=True, timed=True, warm=6) / steps
     assert eng.status() == 0, "fused exchange timed out"
     t = torch.tensor([ms1, msN], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -278,13 +278,16 @@ int pcx_expand_bounds(pcx_engine* e, const double* ocp_x_bnd, const double* y_t0
  * kernel until every launch has been enqueued, so the device-side time does not
  * depend on how fast the host enqueues.  If elapsed_ms is not NULL the call
  * brackets the `count` launches with CUDA events on `stream` (after the gate),
- * synchronises and returns the elapsed time.                                  */
+ * synchronises and returns the elapsed time.  `warm` launches are enqueued first,
+ * in the same call and outside the timed bracket: on a mesh sharded over several
+ * GPUs their in-kernel exchange brings the ranks into step, so the timed launches
+ * do not contain the ranks' start-up skew.                                    */
 typedef struct {
     const double *x, *lam, *sigma;
     double *f, *grad, *c, *dy, *jac, *hess;
 } pcx_args;
 int pcx_eval_many(pcx_engine* e, int what, const pcx_args* sets, int n_sets,
-                  int count, void* stream, int gate, float* elapsed_ms);
+                  int count, int warm, void* stream, int gate, float* elapsed_ms);
 
 /* Sizes (per instance) -- Casadi.evaluate_G_num_nonzero backend.py:1763-1771 */
 int pcx_sizes(const pcx_engine* e, int64_t* num_x, int64_t* num_c, int64_t* num_dy,
@@ -303,6 +306,11 @@ int pcx_host_free(void* ptr);
 /* Number of kernel launches issued by this engine since creation, and the
  * names of the compiled kernel variants (diagnostics for bench.py).          */
 int64_t pcx_launch_count(const pcx_engine* e);
+/* Compiled-kernel facts of the variant for `what` (compiling it if needed): CTAs
+ * resident per SM at the engine's CTA size and shared memory, registers per
+ * thread, local-memory (spill) bytes per thread, static shared memory.        */
+int     pcx_variant_info(pcx_engine* e, int what, int* blocks_per_sm, int* registers,
+                         int* local_bytes, int* static_smem_bytes);
 int     pcx_synchronize(pcx_engine* e, void* stream);
 /* debug: copy the first n doubles of the reduction scratch to the host         */
 int     pcx_debug_read_partials(pcx_engine* e, double* dst, int64_t n);

@@ -375,9 +375,20 @@ PCX_DRAIN(H2VS, h2vs) PCX_DRAIN(H2SS, h2ss) PCX_DRAIN(HTV, htv) PCX_DRAIN(HTS, h
 // (reduction partials, end-node values) or overwrites (gradient zeros) fences
 // those writes and bumps the instance's ticket as soon as its node phase ends.
 // ---------------------------------------------------------------------------
+// The thread's first scatter work item (decoded in the prologue) and the G
+// constants: ONE static block shared by every phase instantiation of pcx_tile
+// (declared inside the template these arrays were allocated once per phase: 20 KB of
+// static shared memory for a 4-phase problem, which cost a resident CTA per SM).
+struct PcxTileStatic {
+    double coef[2 * PCX_THREADS];
+    i64 o[PCX_THREADS];
+    int dp[PCX_THREADS], dstep[PCX_THREADS], ostep[PCX_THREADS], cnt[PCX_THREADS];
+    double cst[1 + 2 * PCX_NY_MAX];
+};
+
 template <class Ph>
 __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
-                         unsigned char* smem_raw)
+                         unsigned char* smem_raw, PcxTileStatic& ts)
 {
     constexpr int F = PCX_FLAGS;
     constexpr int NY = Ph::NY, NV = Ph::NV, NP = Ph::NP, NQ = Ph::NQ, NF = Ph::NF;
@@ -460,10 +471,10 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     int* sAoff = sNodeSec + nn;                                // nsec+1 (prev first): A(N_k) in sB
     int* sWoff = sAoff + (nsec + 1);                           // nsec+1 (prev first): w(N_k) in sB
     // the thread's first scatter work item, decoded in the prologue
-    __shared__ double sPreCoef[2 * T];
-    __shared__ i64 sPreO[T];
-    __shared__ int sPreDp[T], sPreDstep[T], sPreOstep[T], sPreCnt[T];
-    __shared__ double sCst[1 + 2 * (NY > 0 ? NY : 1)];
+    double* sPreCoef = ts.coef;
+    i64* sPreO = ts.o;
+    int *sPreDp = ts.dp, *sPreDstep = ts.dstep, *sPreOstep = ts.ostep, *sPreCnt = ts.cnt;
+    double* sCst = ts.cst;
 
     // ---- table-only part of the prologue (before the dependency wait) --------
     // quadrature table, G constants and the section table slice of the tile go to
@@ -1035,6 +1046,7 @@ extern "C" __global__ void __launch_bounds__(PCX_THREADS, PCX_MIN_BLOCKS)
 PCX_KERNEL_NAME(const __grid_constant__ PcxParams p)
 {
     extern __shared__ __align__(16) unsigned char pcx_smem[];
+    __shared__ PcxTileStatic pcx_tile_static;
     pcx_grid_launch_dependents();
     // large meshes: the border CTA is dispatched first and works in the shadow
     // of the tiles; small ones: last, so that it never holds a slot a tile of
@@ -1070,7 +1082,7 @@ PCX_KERNEL_NAME(const __grid_constant__ PcxParams p)
         }
     }
     switch (phase) {
-#define PCX_CASE(P) case P: pcx_tile<PcxPhase<P> >(p, tile, inst, pcx_smem); break;
+#define PCX_CASE(P) case P: pcx_tile<PcxPhase<P> >(p, tile, inst, pcx_smem, pcx_tile_static); break;
         PCX_FOREACH_PHASE(PCX_CASE)
 #undef PCX_CASE
         default: break;

@@ -107,9 +107,10 @@ def load_library(rebuild=False):
     lib.pcx_structure_hess.argtypes = [vp, i32, dp, dp, dp]
     lib.pcx_jac_row_norms.argtypes = [vp, dp, dp, i32, vp]
     lib.pcx_expand_bounds.argtypes = [vp] + [dp] * 11 + [i32, vp]
-    lib.pcx_eval_many.argtypes = [vp, i32, ctypes.POINTER(_Args), i32, i32, vp, i32,
+    lib.pcx_eval_many.argtypes = [vp, i32, ctypes.POINTER(_Args), i32, i32, i32, vp, i32,
                                   ctypes.POINTER(ctypes.c_float)]
     lib.pcx_status.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
+    lib.pcx_variant_info.argtypes = [vp, i32] + [ctypes.POINTER(ctypes.c_int)] * 4
     _LIB = lib
     return lib
 
@@ -462,16 +463,25 @@ class Engine:
         arr.keepalive = sets
         return arr
 
-    def eval_many(self, what, args, count, stream=None, gate=True, timed=True):
-        """``pcx_eval_many``: ``count`` launches enqueued from C, cycling through the
-        argument sets; returns the device time in ms between the first launch and
-        the end of the last one (CUDA events on ``stream``) when ``timed``."""
+    def eval_many(self, what, args, count, stream=None, gate=True, timed=True, warm=0):
+        """``pcx_eval_many``: ``warm`` untimed + ``count`` timed launches enqueued from
+        C, cycling through the argument sets; returns the device time in ms between
+        the first timed launch and the end of the last one (CUDA events on
+        ``stream``) when ``timed``."""
         ms = ctypes.c_float(0.0)
         self._check(self.lib.pcx_eval_many(
-            self.h, what, args, len(args), int(count),
+            self.h, what, args, len(args), int(count), int(warm),
             ctypes.c_void_p(stream) if stream else None, 1 if gate else 0,
             ctypes.byref(ms) if timed else None), "pcx_eval_many")
         return float(ms.value)
+
+    def variant_info(self, what):
+        """dict(blocks_per_sm, registers, local_bytes, static_smem_bytes) of a variant."""
+        v = [ctypes.c_int(0) for _ in range(4)]
+        self._check(self.lib.pcx_variant_info(self.h, what, *[ctypes.byref(x) for x in v]),
+                    "pcx_variant_info")
+        return dict(zip(("blocks_per_sm", "registers", "local_bytes", "static_smem_bytes"),
+                        (int(x.value) for x in v)), dynamic_smem_bytes=self.smem)
 
     def status(self):
         code = ctypes.c_int(0)

@@ -749,10 +749,17 @@ class NLPStructure:
             if total_nodes >= 32 * sm_count:
                 share = t.N / total_nodes
                 m = max(1, int(np.ceil(want / (sm_count * share))))
+                # resident CTAs per SM: the register cap's figure, or fewer when the
+                # per-node staging of a large body (Delta III: ~500 B per node) makes
+                # shared memory the limit (227 KB per SM, ~8 KB of static + tables)
+                res = resident_ctas(T)
+                stage = self.bytes_per_node(pd) * cap
+                if stage > 40 * 1024:
+                    res = max(1, min(res, (227 * 1024) // (stage + 8 * 1024)))
                 if tiles_per_sm:
                     m = max(m, int(tiles_per_sm))
-                elif m > resident_ctas(T):
-                    m = -(-m // resident_ctas(T)) * resident_ctas(T)   # whole waves
+                elif m > res:
+                    m = -(-m // res) * res                             # whole waves
                 want = max(want, int(round(m * sm_count * share)))
             want = min(want, t.K)
             # the border pass is a CTA of its own (csrc/pcx_kernels.cuh): leave
