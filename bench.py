@@ -368,6 +368,19 @@ def strong_scaling(args, torch, dist, E, rank, world, local_rank):
     torch.cuda.synchronize()
     ms1 = eng.eval_many(what, cargs, steps, stream=st, gate=True, timed=True) / steps
     ref_j, ref_h = jac[(steps - 1) % R].clone(), hes[(steps - 1) % R].clone()
+    # the tiling a single GPU would choose for itself (rank 0 only; the others wait)
+    ms1_own = 0.0
+    if rank == 0 and world > 1:
+        low1, _, _ = lower_case(problems.delta_iii_launch_vehicle(), "lobatto", K, 4, seed=0)
+        eng1 = E.Engine(low1.S, low1.layouts, low1.header, device=local_rank, structure=False)
+        eng1.set_scaling(*scal)
+        a1 = eng1.make_args(sets)
+        eng1.eval_many(what, a1, 3, stream=st, gate=False, timed=False)
+        torch.cuda.synchronize()
+        ms1_own = eng1.eval_many(what, a1, steps, stream=st, gate=True, timed=True) / steps
+        tiles_own = int(low1.S.num_tiles)
+        del eng1, a1, low1
+    dist.barrier()
     # ---- sharded, fused exchange ----------------------------------------------------
     sh = MeshSharder(eng, world, rank, border_rank=0, fused=True)
     jac[0].zero_()
@@ -390,9 +403,10 @@ def strong_scaling(args, torch, dist, E, rank, world, local_rank):
     # ~2 ms timed region, would otherwise be charged to the border rank)
     msN = eng.eval_many(what, cargs, steps, stream=st, gate=True, timed=True, warm=6) / steps
     assert eng.status() == 0, "fused exchange timed out"
-    t = torch.tensor([ms1, msN], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms1, msN, ms1_own], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms1, msN = float(t[0]), float(t[1])
+    ms1, msN, ms1_own = float(t[0]), float(t[1]), float(t[2])
+    best1 = min(ms1, ms1_own) if ms1_own > 0 else ms1
     alg = 8 * (S.num_x + S.nnz_g) + 8 * (S.num_x + S.num_c + S.nnz_h)
     lo, hi = sh.lo, sh.hi
     del jac, hes, ref_j, ref_h
@@ -402,8 +416,11 @@ def strong_scaling(args, torch, dist, E, rank, world, local_rank):
                         % (K, int(sum(t_.N for t_ in S.ph)), world),
             "num_x": int(S.num_x), "nnz_G": int(S.nnz_g), "nnz_H": int(S.nnz_h),
             "tiles": int(S.num_tiles), "tiles_rank0": int(hi - lo),
-            "scaling": "strong", "ms_per_eval_1gpu": ms1, "ms_per_eval": msN,
-            "speedup_vs_1gpu": ms1 / msN, "evals_per_s": 1e3 / msN,
+            "scaling": "strong", "ms_per_eval_1gpu": best1, "ms_per_eval": msN,
+            "speedup_vs_1gpu": best1 / msN, "evals_per_s": 1e3 / msN,
+            "ms_per_eval_1gpu_detail": {"tiling_for_N_gpus": ms1, "tiling_for_1_gpu": ms1_own,
+                                        "note": "speedup is quoted against the faster of the two "
+                                                "unsharded timings"},
             "algorithmic_GBs": alg / msN / 1e6,
             "comm": "fused in-kernel exchange over NVLink peer memory (CUDA IPC mapping of "
                     "the border rank's buffer; st.release.sys / ld.acquire.sys epoch flags, "
