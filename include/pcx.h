@@ -51,6 +51,11 @@ extern "C" {
 #define PCX_EVAL_HESS  8   /* Lagrangian Hessian non-zeros                 */
 #define PCX_EVAL_F     16  /* objective                                    */
 #define PCX_EVAL_GRAD  32  /* objective gradient (dense)                   */
+/* pcx_eval_many only: the argument sets are independent -- no evaluation reads
+ * or overwrites a buffer that one of the 3 preceding evaluations writes (a sweep
+ * over iterates, >= 4 distinct sets).  Consecutive kernels then do not wait for
+ * each other's completion and their load / compute / store phases interleave.  */
+#define PCX_EVAL_INDEPENDENT 256
 
 typedef struct pcx_engine pcx_engine;
 

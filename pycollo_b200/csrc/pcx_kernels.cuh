@@ -549,8 +549,10 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     // ---- the iterate and the multipliers ------------------------------------------
     // everything above touched only the engine's immutable tables; x, lam and
     // every output may belong to the previous kernel in the stream, which has to
-    // be complete from here on
-    pcx_grid_dependency_wait();
+    // be complete from here on -- unless the caller declared the evaluations
+    // independent (distinct buffers, rotating scratch): then consecutive kernels
+    // overlap freely and their load / compute / store phases interleave
+    if (!p.independent) pcx_grid_dependency_wait();
     PCX_STAMP(8);
     double xt0[NV > 0 ? NV : 1];
 #pragma unroll
@@ -886,7 +888,7 @@ __device__ __noinline__ void pcx_border(const PcxParams& p, const int inst, doub
     // the border-value vector lives in shared memory for the whole pass
     double* bv = scratch + 32;
 
-    pcx_grid_dependency_wait();
+    if (!p.independent) pcx_grid_dependency_wait();
     // ---- independent of the tiles ------------------------------------------
     for (int a = tid; a < PCX_NPOINT; a += T) {
         const double v = pcx_unscale(p.pt_scal[a], x[p.pt_x[a]], p.pt_scal[PCX_NPOINT + a]);

@@ -63,7 +63,11 @@ struct PcxParams {
     // consumed it: a rank can run at most two evaluations ahead.
     double* peer_xbuf; unsigned long long* peer_flags; unsigned long long* peer_done;
     unsigned long long epoch;
-    int rank, world, border_rank, pad1;
+    // independent != 0: the caller declared that this evaluation neither reads nor
+    // overwrites anything the previous evaluation on the stream writes (a sweep over
+    // iterates with distinct buffers): the kernel does not wait for that grid to
+    // complete before touching its own data (scratch sets rotate on the host side)
+    int rank, world, border_rank, independent;
     u32* status;            // sticky device-side error word (0 = ok; 1 = exchange timeout)
     // tiles
     const i64* tile_desc;   // 8 per tile: phase,k0,k1,node0,nn,run0,run1,-

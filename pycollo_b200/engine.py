@@ -17,6 +17,7 @@ from . import build as _build
 
 PCX_HOST, PCX_DEVICE = 0, 1
 EVAL_C, EVAL_DY, EVAL_JAC, EVAL_HESS, EVAL_F, EVAL_GRAD = 1, 2, 4, 8, 16, 32
+EVAL_INDEPENDENT = 256        # pcx_eval_many: the argument sets are independent
 
 _LIB = None
 

@@ -152,6 +152,39 @@ def test_device_pointers_and_determinism(cuda_device):
         assert np.array_equal(jac.cpu().numpy(), j1) and np.array_equal(hes.cpu().numpy(), h1)
 
 
+def test_independent_sweep_is_bitwise_the_ordered_result(cuda_device):
+    """``pcx_eval_many(PCX_EVAL_INDEPENDENT)``: evaluations declared independent are not
+    ordered against each other on the device (no dependency wait, rotating scratch
+    sets); every one of them must still produce exactly what stream order produces."""
+    import torch
+    for name, K in (("cart_pole_swing_up", 6000), ("multiphase_sliding_mass", 900)):
+        low, _, scal = build_case(getattr(examples, name)(), "lobatto", K, 4, seed=5, oracle=False)
+        eng = make_engine(low, scal)
+        S = low.S
+        what = E.EVAL_JAC | E.EVAL_HESS | E.EVAL_C | E.EVAL_F | E.EVAL_GRAD
+        g = torch.Generator(device="cuda").manual_seed(3)
+        z = lambda n: torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+        sets = [dict(x=torch.rand(S.num_x, dtype=torch.float64, device="cuda", generator=g) - 0.5,
+                     lam=torch.randn(S.num_c, dtype=torch.float64, device="cuda", generator=g),
+                     f=z(1), grad=z(S.num_x), c=z(S.num_c), jac=z(S.nnz_g), hess=z(S.nnz_h))
+                for _ in range(5)]
+        args = eng.make_args(sets)
+        st = torch.cuda.current_stream().cuda_stream
+        eng.eval_many(what, args, 5, stream=st, gate=False, timed=False)
+        torch.cuda.synchronize()
+        ref = [{k: s[k].clone() for k in ("f", "grad", "c", "jac", "hess")} for s in sets]
+        for s in sets:
+            for k in ("f", "grad", "c", "jac", "hess"):
+                s[k].fill_(float("nan"))
+        eng.eval_many(what | E.EVAL_INDEPENDENT, args, 35, stream=st, gate=True, timed=True)
+        torch.cuda.synchronize()
+        for s, r in zip(sets, ref):
+            for k, v in r.items():
+                assert torch.equal(s[k], v), (name, k)
+    with pytest.raises(E.PcxError, match="distinct argument sets"):
+        eng.eval_many(what | E.EVAL_INDEPENDENT, eng.make_args(sets[:2]), 4, stream=st)
+
+
 @pytest.mark.parametrize("method", ["lobatto", "radau"])
 def test_full_size_config2_properties(method, cuda_device):
     """BASELINE config 2 (cart-pole, 10^5 nodes) under both schemes -- Radau is the

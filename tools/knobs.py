@@ -30,6 +30,13 @@ eng.eval_many(what, args, 20, stream=st, gate=False, timed=False)
 torch.cuda.synchronize()
 best = min(eng.eval_many(what, args, 200, stream=st, gate=True, timed=True) for _ in range(3)) / 200
 short = min(eng.eval_many(what, args, 20, stream=st, gate=True, timed=True) for _ in range(3)) / 20
+indep = min(eng.eval_many(what | E.EVAL_INDEPENDENT, args, 200, stream=st, gate=True, timed=True) for _ in range(3)) / 200
+indep20 = min(eng.eval_many(what | E.EVAL_INDEPENDENT, args, 20, stream=st, gate=True, timed=True) for _ in range(3)) / 20
+# results of the overlapped launches must equal the ordered ones
+ref = [s["jac"].clone() for s in sets], [s["hess"].clone() for s in sets]
+eng.eval_many(what, args, R, stream=st, gate=False, timed=False)
+torch.cuda.synchronize()
+same = all(torch.equal(a, s["jac"]) for a, s in zip(ref[0], sets)) and all(torch.equal(a, s["hess"]) for a, s in zip(ref[1], sets))
 one = [eng.make_args([s]) for s in sets]
 lat = []
 for i in range(30):
@@ -41,4 +48,6 @@ print(json.dumps(dict(label=label, tiles=int(S.num_tiles), threads=int(S.threads
                       frac_200=round(alg / (best * 1e-3) / 6553e9, 4),
                       frac_20=round(alg / (short * 1e-3) / 6553e9, 4),
                       latency_us=round(1e3 * float(np.median(lat[5:])), 3),
+                      us_independent_200=round(1e3 * indep, 3), us_independent_20=round(1e3 * indep20, 3),
+                      frac_independent_20=round(alg / (indep20 * 1e-3) / 6553e9, 4), independent_equal=bool(same),
                       env={k: v for k, v in os.environ.items() if k.startswith("PCX_")})), flush=True)
