@@ -519,7 +519,11 @@ def run_cuda(args):
     hj = torch.empty(S.nnz_g, dtype=torch.float64).pin_memory()
     hh = torch.empty(S.nnz_h, dtype=torch.float64).pin_memory()
     e2e_steps = max(3, min(steps, 50))
-    call = eng.bind(what, hx, lam=hl, sigma=hs, jac=hj, hess=hh, space=E.PCX_HOST, stream=stream)
+    # the host keeps its value arrays between evaluations (a solver's buffers), so the
+    # Jacobian slots that do not depend on the iterate are fetched once, not every step
+    # (PCX_EVAL_CONST_RESIDENT; the bytes actually copied are reported)
+    call = eng.bind(what | E.EVAL_CONST_RESIDENT, hx, lam=hl, sigma=hs, jac=hj, hess=hh,
+                    space=E.PCX_HOST, stream=stream)
     for _ in range(3):
         call()
     barrier()
@@ -530,13 +534,25 @@ def run_cuda(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     launches += eng.launch_count - l1
+    e2e_d2h = eng.last_d2h_bytes
+    # the same without the promise: every value crosses PCIe every step
+    call_full = eng.bind(what, hx, lam=hl, sigma=hs, jac=hj, hess=hh, space=E.PCX_HOST, stream=stream)
+    for _ in range(2):
+        call_full()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        call_full()
+    torch.cuda.synchronize()
+    e2e_full_s = time.perf_counter() - t0
+    launches += 2 * (e2e_steps + 2)
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([ms, 1e3 * e2e_s, float(np.median(lat)), ms_ordered], dtype=torch.float64,
-                     device=dev)
+    t = torch.tensor([ms, 1e3 * e2e_s, float(np.median(lat)), ms_ordered, 1e3 * e2e_full_s],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max, lat_us, ms_ord = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    ms_max, e2e_ms_max, lat_us, ms_ord, e2e_full_ms = (float(v) for v in t)
 
     strong = None
     if world > 1 and not args.no_strong:
@@ -588,9 +604,15 @@ def run_cuda(args):
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT,
                         "h2d_bytes_per_step": 8 * (S.num_x + S.num_c + 1),
-                        "d2h_bytes_per_step": 8 * (S.nnz_g + S.nnz_h),
-                        "steps": e2e_steps, "api": "pcx_eval(..., PCX_HOST) on pinned "
-                                                   "host buffers"},
+                        "d2h_bytes_per_step": int(e2e_d2h),
+                        "steps": e2e_steps,
+                        "api": "pcx_eval(JAC|HESS|CONST_RESIDENT, PCX_HOST) on pinned host buffers: "
+                               "the host's value arrays persist between evaluations, so the "
+                               "iterate-independent Jacobian slots (whole variable blocks; listed "
+                               "by the structure builder) are fetched by the first evaluation only",
+                        "all_values_every_step": {
+                            "value": world * e2e_steps / (e2e_full_ms * 1e-3), "unit": UNIT,
+                            "d2h_bytes_per_step": 8 * (S.nnz_g + S.nnz_h)}},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "amortised": amortised}
         if strong is not None:

@@ -56,6 +56,15 @@ extern "C" {
  * over iterates, >= 4 distinct sets).  Consecutive kernels then do not wait for
  * each other's completion and their load / compute / store phases interleave.  */
 #define PCX_EVAL_INDEPENDENT 256
+/* PCX_HOST evaluations of the Jacobian only: the caller's `jac` array still holds
+ * what the previous host-space evaluation of this engine left in it.  Slots that do
+ * not depend on the iterate (the +-1 entries of the difference operator; with fixed
+ * phase times also h/2*I[l,m] entries of equations like dq/dt = qd -- whole variable
+ * blocks, listed in the optional table "g_const_ranges") are then fetched only by the
+ * first evaluation into that array after pcx_set_scaling; later ones copy the
+ * iterate-dependent runs only (cart-pole: 20 % fewer PCIe bytes).  Passing another
+ * array, or calling pcx_set_scaling, makes the next evaluation fetch everything.   */
+#define PCX_EVAL_CONST_RESIDENT 512
 
 typedef struct pcx_engine pcx_engine;
 
@@ -311,6 +320,8 @@ int pcx_host_free(void* ptr);
 /* Number of kernel launches issued by this engine since creation, and the
  * names of the compiled kernel variants (diagnostics for bench.py).          */
 int64_t pcx_launch_count(const pcx_engine* e);
+/* Jacobian + Hessian bytes the last PCX_HOST evaluation copied device -> host      */
+int64_t pcx_last_d2h_bytes(const pcx_engine* e);
 /* Compiled-kernel facts of the variant for `what` (compiling it if needed): CTAs
  * resident per SM at the engine's CTA size and shared memory, registers per
  * thread, local-memory (spill) bytes per thread, static shared memory.        */

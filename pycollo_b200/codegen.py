@@ -42,8 +42,8 @@ class _CudaPrinter(C99CodePrinter):
         if exp == sym.Rational(1, 2):
             return f"sqrt({self._print(base)})"
         if exp == sym.Rational(-1, 2):
-            return f"rsqrt({self._print(base)})" if False else \
-                f"(1.0/sqrt({self._print(base)}))"
+            # IEEE division of a correctly rounded sqrt (rsqrt() is not correctly rounded)
+            return f"(1.0/sqrt({self._print(base)}))"
         return f"pow({self._print(base)}, {self._print(exp)})"
 
     def _print_Symbol(self, expr):

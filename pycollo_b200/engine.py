@@ -18,6 +18,7 @@ from . import build as _build
 PCX_HOST, PCX_DEVICE = 0, 1
 EVAL_C, EVAL_DY, EVAL_JAC, EVAL_HESS, EVAL_F, EVAL_GRAD = 1, 2, 4, 8, 16, 32
 EVAL_INDEPENDENT = 256        # pcx_eval_many: the argument sets are independent
+EVAL_CONST_RESIDENT = 512     # PCX_HOST: the jac array keeps its iterate-independent slots
 
 _LIB = None
 
@@ -90,6 +91,8 @@ def load_library(rebuild=False):
     lib.pcx_host_free.argtypes = [vp]
     lib.pcx_launch_count.argtypes = [vp]
     lib.pcx_launch_count.restype = i64
+    lib.pcx_last_d2h_bytes.argtypes = [vp]
+    lib.pcx_last_d2h_bytes.restype = i64
     lib.pcx_synchronize.argtypes = [vp, vp]
     lib.pcx_flush_l2.argtypes = [vp, i64, vp]
     lib.pcx_set_shard.argtypes = [vp, i32, i32]
@@ -329,6 +332,9 @@ class Engine:
             gr, gc = S.G_structure()
             hr, hc = S.H_structure()
             extra = [(b"g_rows", gr), (b"g_cols", gc), (b"h_rows", hr), (b"h_cols", hc)]
+            cr = S.G_constant_ranges()
+            if len(cr):
+                extra.append((b"g_const_ranges", cr.ravel()))
         arr = (_Table * (n + len(extra)))()
         self._keep = []
         for i in range(n):
@@ -635,6 +641,10 @@ class Engine:
     def synchronize(self, stream=None):
         self._check(self.lib.pcx_synchronize(
             self.h, ctypes.c_void_p(stream) if stream else None), "pcx_synchronize")
+
+    @property
+    def last_d2h_bytes(self):
+        return int(self.lib.pcx_last_d2h_bytes(self.h))
 
     @property
     def launch_count(self):

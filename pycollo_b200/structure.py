@@ -32,6 +32,12 @@ import os
 
 import numpy as np
 
+
+def sym_free(expr):
+    """Free symbols of a sympy expression (empty for plain numbers)."""
+    return getattr(expr, "free_symbols", ())
+
+
 # recipe word bit layout (must match csrc/pcx_params.h).  Low word: staged row
 # (9 bits), quadrature-table index (13), constant index (7), three flags; high
 # word: variable (8), slot inside the variable's period (18), node inside the
@@ -523,6 +529,50 @@ class NLPStructure:
         self.type_var_off = np.asarray(self.type_var_off, dtype=np.int32)
         self._g_parts = (g_rows_parts, g_cols_parts, g_slot_parts)
         self._G_rows = self._G_cols = None
+
+    def G_constant_ranges(self, min_len=4096):
+        """Maximal runs ``[lo, hi)`` of Jacobian value slots that do NOT depend on the
+        iterate (only on the mesh and the scaling), at least ``min_len`` slots long.
+
+        A slot of a (y, u) column is constant when it holds no staged derivative (the
+        +-1 entries of the difference operator) or when its derivative expression is a
+        number and nothing iterate-dependent multiplies it: with fixed phase times
+        ``dq/dt = qd`` contributes ``h/2 * I[l, m]`` -- a constant of the mesh.  Whole
+        variable blocks are constant for such states (cart-pole: the q1 and q1d
+        columns, 20 % of the Jacobian), and a host that keeps its value array between
+        evaluations need not fetch them again (``PCX_EVAL_CONST_RESIDENT``).
+        Slots outside the (y, u) columns, entries written by the border pass and
+        everything in a phase with a free time are treated as iterate-dependent."""
+        mask = np.zeros(self.nnz_g, dtype=bool)
+        for ip, (pd, t) in enumerate(zip(self.pd, self.ph)):
+            free_time = t.t_cols[0] >= 0 or t.t_cols[1] >= 0
+            number = [len(sym_free(e)) == 0 for e in pd.d1v_expr]
+            for a in range(pd.NV):
+                for lt, tid in enumerate(t.type_ids):
+                    ents = self.type_recipes[tid][a]
+                    if not ents:
+                        continue
+                    flags = np.zeros(len(ents), dtype=bool)
+                    for ie, ent in enumerate(ents):
+                        st, skip = ent[5], ent[9]
+                        if skip:
+                            continue
+                        if st == 0:
+                            flags[ie] = True
+                        else:
+                            fam = pd.fam[pd.d1v[st - 1][0]]
+                            flags[ie] = number[st - 1] and (fam == "p" or not free_time)
+                    if not flags.any():
+                        continue
+                    ks = np.flatnonzero(t.sec_type_local == lt)
+                    sl = t.gsec_ptr[a, ks][:, None] + np.arange(len(ents))[None, :]
+                    mask[sl[:, flags].ravel()] = True
+        if not mask.any():
+            return np.zeros((0, 2), dtype=np.int64)
+        d = np.diff(np.concatenate([[0], mask.view(np.int8), [0]]))
+        lo, hi = np.flatnonzero(d == 1), np.flatnonzero(d == -1)
+        keep = (hi - lo) >= int(min_len)
+        return np.stack([lo[keep], hi[keep]], axis=1).astype(np.int64)
 
     def _g_explicit(self, rp, cp, sp, slot, row, col):
         rp.append(np.array([row], dtype=np.int64))

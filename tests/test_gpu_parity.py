@@ -152,6 +152,43 @@ def test_device_pointers_and_determinism(cuda_device):
         assert np.array_equal(jac.cpu().numpy(), j1) and np.array_equal(hes.cpu().numpy(), h1)
 
 
+def test_const_resident_host_evaluation(cuda_device):
+    """``PCX_EVAL_CONST_RESIDENT``: a host array that persists between evaluations gets
+    its iterate-independent Jacobian slots once; later evaluations copy the other runs
+    only -- and the array must still equal a full evaluation, also after a change of
+    scaling and when another array is passed."""
+    low, B, scal = build_case(examples.cart_pole_swing_up(), "lobatto", 4000, 4, seed=5)
+    S = low.S
+    ranges = S.G_constant_ranges()
+    n_const = int((ranges[:, 1] - ranges[:, 0]).sum())
+    assert n_const > 0.15 * S.nnz_g                      # the q1 / q1d columns
+    eng = make_engine(low, scal)
+    rng = np.random.default_rng(1)
+    what = E.EVAL_JAC | E.EVAL_HESS
+    jac, hes = np.full(S.nnz_g, np.nan), np.full(S.nnz_h, np.nan)
+    other = np.full(S.nnz_g, np.nan)
+
+    def run(flags, x, lam, out_j):
+        eng._check(eng.lib.pcx_eval(eng.h, flags, E._ptr(x), E._ptr(lam), None, None, None, None,
+                                    None, E._ptr(out_j), E._ptr(hes), E.PCX_HOST, None), "pcx_eval")
+        return eng.last_d2h_bytes
+
+    for k in range(4):
+        x, lam = rng.uniform(-0.5, 0.5, S.num_x), rng.standard_normal(S.num_c)
+        nbytes = run(what | E.EVAL_CONST_RESIDENT, x, lam, jac)
+        full = 8 * (S.nnz_g + S.nnz_h)
+        assert nbytes == (full if k == 0 else full - 8 * n_const)
+        ref = eng.eval_host(what, x, lam, 1.0)
+        assert np.array_equal(jac, ref["jac"][0]) and np.array_equal(hes, ref["hess"][0])
+        assert max_err(jac, B.G_nonzeros(x)) <= RTOL
+    assert run(what | E.EVAL_CONST_RESIDENT, x, lam, other) == full      # another array: everything
+    assert np.array_equal(other, jac)
+    eng.set_scaling(scal[0], scal[1], 2.0 * scal[2], scal[3])            # new scaling: everything
+    assert run(what | E.EVAL_CONST_RESIDENT, x, lam, other) == full
+    assert np.array_equal(other, eng.eval_host(E.EVAL_JAC, x)["jac"][0])
+    assert run(E.EVAL_JAC | E.EVAL_CONST_RESIDENT, x, lam, other) == 8 * (S.nnz_g - n_const)
+
+
 def test_independent_sweep_is_bitwise_the_ordered_result(cuda_device):
     """``pcx_eval_many(PCX_EVAL_INDEPENDENT)``: evaluations declared independent are not
     ordered against each other on the device (no dependency wait, rotating scratch
