@@ -222,6 +222,17 @@ class PhaseLayout:
         self.nred = self.red_hss + len(pd.h2ss)
 
 
+def stage_h_rule(n_h2vv):
+    """Stage the node-diagonal Hessian entries through shared memory?  Measured on
+    Delta III (37 entries per node, 10^6 nodes): 0.53-0.65 ms with staging against
+    0.47 ms with direct stores in every tiling tried -- the partial-sector stores are
+    merged in L2 and the extra shared memory costs a resident CTA -- so the answer is
+    no; ``PCX_STAGE_H=1`` keeps the experiment reproducible (correct: the GPU suite
+    passes with it)."""
+    import os
+    return bool(int(os.environ.get("PCX_STAGE_H", "0"))) and n_h2vv > 0
+
+
 def generate(ir, phase_derivs, point_derivs, structure):
     """Return (header_source, layouts)."""
     P = len(ir.phases)
@@ -299,6 +310,14 @@ def _phase_struct(q, ph, pd, lay, NS):
     s.append(_cfun("H2VV_B", [b for _, b in pd.h2vv]))
     s.append(_cfun("H2VV_POS", pos))
     s.append(_cfun("NA", nA))
+    # experiment (off by default, see stage_h_rule): node-diagonal Hessian entries staged
+    # in shared memory (one row of HP doubles per node, odd stride) and written one
+    # variable block at a time, coalesced
+    hb_off = [sum(nA[:b]) for b in range(NV)]
+    stage_h = stage_h_rule(len(pd.h2vv))
+    s.append(f"    static constexpr bool STAGE_H = {'true' if stage_h else 'false'};\n")
+    s.append(f"    static constexpr int HP = {(len(pd.h2vv) | 1) if stage_h else 0};\n")
+    s.append(_cfun("HB_OFF", hb_off))
 
     # ---- the expression body ----
     vsyms = [sym.Symbol(f"v{a}") for a in range(NV + NS)]

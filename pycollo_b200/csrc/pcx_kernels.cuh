@@ -254,6 +254,7 @@ struct PcxNodeSink {
 
     const double* ps; const i64* pb;
     double *sF, *sD, *sDS, *sDP;          // already offset by the node / section
+    double* sH;                           // this node's row of staged Hessian entries
     int nnp, nsp;
     bool sec_start, owned, regular;
     double hp, wq, h_k, h_pr;
@@ -304,11 +305,15 @@ struct PcxNodeSink {
     }
     template <int K> __device__ __forceinline__ void H2VV(const double val) const {
         if (!WANT_H || !owned) return;
-        if (regular)
-            out_h[pb[Ph::PB_HREG + Ph::H2VV_B(K)] + (m - 1) * Ph::NA(Ph::H2VV_B(K))
-                  + Ph::H2VV_POS(K)] = ps[Ph::OFF_H2VV + K] * val;
-        else
+        if (regular) {
+            if (Ph::STAGE_H)
+                sH[Ph::HB_OFF(Ph::H2VV_B(K)) + Ph::H2VV_POS(K)] = ps[Ph::OFF_H2VV + K] * val;
+            else
+                out_h[pb[Ph::PB_HREG + Ph::H2VV_B(K)] + (m - 1) * Ph::NA(Ph::H2VV_B(K))
+                      + Ph::H2VV_POS(K)] = ps[Ph::OFF_H2VV + K] * val;
+        } else {
             irr[K] = val;
+        }
     }
     template <int K> __device__ __forceinline__ void H2VS(const double val) const {
         if (!WANT_H || !owned) return;
@@ -385,6 +390,28 @@ struct PcxTileStatic {
     int dp[PCX_THREADS], dstep[PCX_THREADS], ostep[PCX_THREADS], cnt[PCX_THREADS];
     double cst[1 + 2 * PCX_NY_MAX];
 };
+
+// Staged node-diagonal Hessian entries -> global memory, one variable block at a
+// time: the block's slots of the tile's regular nodes are contiguous
+// (NA(b) per node), consecutive threads write consecutive doubles.
+template <class Ph, int... Bs>
+__device__ __forceinline__ void pcx_flush_h(const double* sH, double* out_h, const i64* pb,
+                                            const i64 m_first, const int a0, const int n_reg,
+                                            const int tid, PcxSeq<Bs...>) {
+    constexpr int T = PCX_THREADS;
+    int dummy[] = {0, ([&] {
+        constexpr int NAb = Ph::NA(Bs);
+        if (NAb > 0) {
+            double* dst = out_h + pb[Ph::PB_HREG + Bs] + (m_first - 1) * NAb;
+            const double* src = sH + a0 * Ph::HP + Ph::HB_OFF(Bs);
+            for (int i = tid; i < n_reg * NAb; i += T) {
+                const int nd = i / NAb;
+                dst[i] = src[nd * Ph::HP + (i - nd * NAb)];
+            }
+        }
+    }(), 0)...};
+    (void)dummy;
+}
 
 template <class Ph>
 __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
@@ -464,7 +491,8 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     double* sDS = sDP + (WANT_G ? Ph::ND1V * nsp : 0);         // NDS * nnp
     double* sLam = sDS + (WANT_G ? NDS * nnp : 0);             // NY * (nn + PCX_LAM_HALO)
     const int lam_stride = nn + PCX_LAM_HALO;
-    double* sRed = sLam + (WANT_H ? NY * lam_stride : 0);      // T/32
+    double* sH = sLam + (WANT_H ? NY * lam_stride : 0);        // HP * nn (staged H entries)
+    double* sRed = sH + ((WANT_H && Ph::STAGE_H) ? Ph::HP * nn : 0);   // T/32
     int* sSecNode = reinterpret_cast<int*>(sRed + T / 32);     // nsec+2 (prev first)
     int* sSecOrder = sSecNode + (nsec + 2);                    // nsec+1 (prev first)
     int* sNodeSec = sSecOrder + (nsec + 1);                    // nn
@@ -669,6 +697,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         PcxNodeSink<Ph> sink;
         sink.ps = ps; sink.pb = pb;
         sink.sF = sF + ml; sink.sD = sD + ml; sink.sDS = sDS + ml; sink.sDP = sDP + s;
+        sink.sH = sH + ml * Ph::HP;
         sink.nnp = nnp; sink.nsp = nsp; sink.sec_start = (mloc == 0);
         sink.hp = hp; sink.wq = wq; sink.h_k = h_k; sink.h_pr = h_pr;
         sink.owned = owned; sink.regular = (m != 0) && (m != N - 1);
@@ -735,6 +764,12 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         if (WANT_GRAD || tid == 0 || (active && (m_me == 0 || m_me == N - 1))) __threadfence();
         __syncthreads();
         if (tid == 0) atomicAdd(p.ticket + inst, 1u);
+    }
+    // ---- staged Hessian entries of the tile's regular nodes, block by block ------
+    if (WANT_H && Ph::STAGE_H) {
+        const int a0 = (node0 == 0) ? 1 : 0;               // node 0 / N-1 go through irr
+        pcx_flush_h<Ph>(sH, out_h, pb, node0 + a0, a0, (nn - 1) - a0, tid,
+                        typename PcxMakeSeq<NV>::type());
     }
     // ---- row-oriented contractions: defect rows of c, t/s columns of G -------
     if (NEED_ROWS) {

@@ -283,9 +283,11 @@ def smem_bytes(S, layouts, threads):
     for lay in layouts:
         pd = lay.pd
         nds = sum(1 for e, _ in pd.d1s if pd.fam[e] == "d")
+        from .codegen import stage_h_rule
+        hp = (len(pd.h2vv) | 1) if stage_h_rule(len(pd.h2vv)) else 0
         dbl = (len(S.btab) + SS + 1 + (pd.NY + len(pd.d1v) + nds) * (NN | 1)
                + len(pd.d1v) * (SS + 1)
-               + pd.NY * (NN + 24) + threads // 32 + 2)      # PCX_LAM_HALO
+               + pd.NY * (NN + 24) + hp * NN + threads // 32 + 2)      # PCX_LAM_HALO
         ints = (SS + 2) + (SS + 1) + NN + 2 * (SS + 1) + 8
         best = max(best, 8 * dbl + 4 * ints)
     best = max(best, 8 * (32 + S.bv_size))      # border pass: scratch + BV

@@ -782,8 +782,10 @@ class NLPStructure:
     # -------------------------------------------------------------- tiles --
     def bytes_per_node(self, pd):
         """Shared-memory doubles staged per node (see csrc/pcx_kernels.cuh)."""
+        from .codegen import stage_h_rule
+        hp = (len(pd.h2vv) | 1) if stage_h_rule(len(pd.h2vv)) else 0
         return 8 * (pd.NY + len(pd.d1v) + 1 + sum(1 for e, _ in pd.d1s
-                                                  if pd.fam[e] == "d") + 2)
+                                                  if pd.fam[e] == "d") + 2 + hp)
 
     def _build_tiles(self, sm_count, max_tile_nodes, smem_budget, tiles_per_sm=None):
         T = self.threads
