@@ -546,13 +546,30 @@ def run_cuda(args):
     torch.cuda.synchronize()
     e2e_full_s = time.perf_counter() - t0
     launches += 2 * (e2e_steps + 2)
+    # a sweep over iterates with a host consumer (multi-start): the same host-space
+    # evaluations pipelined by pcx_sweep_host -- the upload of step i+1 and the kernel
+    # of step i run under the download of step i-1 (PCIe is full duplex).  Every step
+    # still uploads its inputs from pinned memory and downloads its values.
+    hsets = [dict(x=hx, lam=hl, sigma=hs, jac=hj, hess=hh),
+             dict(x=torch.from_numpy(rng.uniform(-0.5, 0.5, S.num_x)).pin_memory(),
+                  lam=torch.from_numpy(rng.standard_normal(S.num_c)).pin_memory(), sigma=hs,
+                  jac=torch.empty(S.nnz_g, dtype=torch.float64).pin_memory(),
+                  hess=torch.empty(S.nnz_h, dtype=torch.float64).pin_memory())]
+    hargs = eng.make_args(hsets)
+    eng.sweep_host(what | E.EVAL_CONST_RESIDENT, hargs, 4, stream=stream)
+    barrier()
+    t0 = time.perf_counter()
+    eng.sweep_host(what | E.EVAL_CONST_RESIDENT, hargs, e2e_steps, stream=stream)
+    torch.cuda.synchronize()
+    e2e_sweep_s = time.perf_counter() - t0
+    launches += e2e_steps + 4
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([ms, 1e3 * e2e_s, float(np.median(lat)), ms_ordered, 1e3 * e2e_full_s],
-                     dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, 1e3 * e2e_s, float(np.median(lat)), ms_ordered, 1e3 * e2e_full_s,
+                      1e3 * e2e_sweep_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max, lat_us, ms_ord, e2e_full_ms = (float(v) for v in t)
+    ms_max, e2e_ms_max, lat_us, ms_ord, e2e_full_ms, e2e_sweep_ms = (float(v) for v in t)
 
     strong = None
     if world > 1 and not args.no_strong:
@@ -565,7 +582,8 @@ def run_cuda(args):
 
     if rank == 0:
         value = world * steps / (ms_max * 1e-3)
-        e2e_value = world * e2e_steps / (e2e_ms_max * 1e-3)
+        e2e_seq_value = world * e2e_steps / (e2e_ms_max * 1e-3)
+        e2e_value = world * e2e_steps / (e2e_sweep_ms * 1e-3)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
@@ -606,10 +624,17 @@ def run_cuda(args):
                         "h2d_bytes_per_step": 8 * (S.num_x + S.num_c + 1),
                         "d2h_bytes_per_step": int(e2e_d2h),
                         "steps": e2e_steps,
-                        "api": "pcx_eval(JAC|HESS|CONST_RESIDENT, PCX_HOST) on pinned host buffers: "
-                               "the host's value arrays persist between evaluations, so the "
-                               "iterate-independent Jacobian slots (whole variable blocks; listed "
-                               "by the structure builder) are fetched by the first evaluation only",
+                        "api": "pcx_sweep_host(JAC|HESS|CONST_RESIDENT) over pinned host argument "
+                               "sets: a stream of independent iterates with a host consumer, "
+                               "pipelined (upload of step i+1 and kernel of step i under the "
+                               "download of step i-1).  The host's value arrays persist between "
+                               "evaluations, so the iterate-independent Jacobian slots (whole "
+                               "variable blocks; listed by the structure builder) are fetched by "
+                               "the first evaluation into an array only",
+                        "sequential": {
+                            "value": e2e_seq_value, "unit": UNIT,
+                            "api": "one blocking pcx_eval(JAC|HESS|CONST_RESIDENT, PCX_HOST) per "
+                                   "step: what a sequential solver sees"},
                         "all_values_every_step": {
                             "value": world * e2e_steps / (e2e_full_ms * 1e-3), "unit": UNIT,
                             "d2h_bytes_per_step": 8 * (S.nnz_g + S.nnz_h)}},

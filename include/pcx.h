@@ -303,6 +303,15 @@ typedef struct {
 int pcx_eval_many(pcx_engine* e, int what, const pcx_args* sets, int n_sets,
                   int count, int warm, void* stream, int gate, float* elapsed_ms);
 
+/* Host-space sweep over iterates (multi-start / parameter sweep with a host
+ * consumer): `count` evaluations of PCX_EVAL_JAC or PCX_EVAL_JAC | PCX_EVAL_HESS
+ * cycling through `n_sets` >= 2 HOST argument sets (pinned memory for full PCIe
+ * speed), pipelined -- the upload of evaluation i+1 and the kernel of evaluation i
+ * run under the download of evaluation i-1.  Returns when every result is in its
+ * host arrays.  PCX_EVAL_CONST_RESIDENT applies per host jac array.             */
+int pcx_sweep_host(pcx_engine* e, int what, const pcx_args* sets, int n_sets, int count,
+                   void* stream);
+
 /* Sizes (per instance) -- Casadi.evaluate_G_num_nonzero backend.py:1763-1771 */
 int pcx_sizes(const pcx_engine* e, int64_t* num_x, int64_t* num_c, int64_t* num_dy,
               int64_t* nnz_jac, int64_t* nnz_hess, int32_t* batch);

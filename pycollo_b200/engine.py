@@ -113,6 +113,7 @@ def load_library(rebuild=False):
     lib.pcx_expand_bounds.argtypes = [vp] + [dp] * 11 + [i32, vp]
     lib.pcx_eval_many.argtypes = [vp, i32, ctypes.POINTER(_Args), i32, i32, i32, vp, i32,
                                   ctypes.POINTER(ctypes.c_float)]
+    lib.pcx_sweep_host.argtypes = [vp, i32, ctypes.POINTER(_Args), i32, i32, vp]
     lib.pcx_status.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
     lib.pcx_variant_info.argtypes = [vp, i32] + [ctypes.POINTER(ctypes.c_int)] * 4
     _LIB = lib
@@ -483,6 +484,13 @@ class Engine:
             ctypes.c_void_p(stream) if stream else None, 1 if gate else 0,
             ctypes.byref(ms) if timed else None), "pcx_eval_many")
         return float(ms.value)
+
+    def sweep_host(self, what, args, count, stream=None):
+        """``pcx_sweep_host``: ``count`` pipelined host-space evaluations cycling through
+        the (>= 2) host argument sets of ``make_args``; blocks until all are done."""
+        self._check(self.lib.pcx_sweep_host(
+            self.h, what, args, len(args), int(count),
+            ctypes.c_void_p(stream) if stream else None), "pcx_sweep_host")
 
     def variant_info(self, what):
         """dict(blocks_per_sm, registers, local_bytes, static_smem_bytes) of a variant."""

@@ -189,6 +189,38 @@ def test_const_resident_host_evaluation(cuda_device):
     assert run(E.EVAL_JAC | E.EVAL_CONST_RESIDENT, x, lam, other) == 8 * (S.nnz_g - n_const)
 
 
+def test_pipelined_host_sweep(cuda_device):
+    """``pcx_sweep_host``: pipelined host-space evaluations (upload / kernel / download
+    of consecutive iterates overlap) leave in every host set exactly what one blocking
+    ``pcx_eval`` per iterate leaves, with and without PCX_EVAL_CONST_RESIDENT."""
+    import torch
+    low, _, scal = build_case(examples.cart_pole_swing_up(), "lobatto", 5000, 4, seed=5, oracle=False)
+    eng = make_engine(low, scal)
+    S = low.S
+    what = E.EVAL_JAC | E.EVAL_HESS
+    rng = np.random.default_rng(4)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    n_const = int(np.diff(S.G_constant_ranges(), axis=1).sum())
+    for flags in (what, what | E.EVAL_CONST_RESIDENT):
+        sets = [dict(x=pin(rng.uniform(-0.5, 0.5, S.num_x)), lam=pin(rng.standard_normal(S.num_c)),
+                     sigma=pin(np.array([0.5 + k])), jac=pin(np.full(S.nnz_g, np.nan)),
+                     hess=pin(np.full(S.nnz_h, np.nan))) for k in range(3)]
+        args = eng.make_args(sets)
+        for count in (7, 3):                          # second round: constants already resident
+            eng.sweep_host(flags, args, count)
+            if flags & E.EVAL_CONST_RESIDENT:
+                full = 8 * (S.nnz_g + S.nnz_h)
+                assert eng.last_d2h_bytes == (full - 8 * n_const if n_const else full)
+            for s_ in sets:
+                # (the blocking call runs the Jacobian-only and Hessian-only variants, the
+                # sweep the fused one: separate compilations, rounding-level differences)
+                ref = eng.eval_host(what, s_["x"].numpy(), s_["lam"].numpy(), float(s_["sigma"][0]))
+                assert max_err(s_["jac"].numpy(), ref["jac"][0]) <= 1e-13
+                assert max_err(s_["hess"].numpy(), ref["hess"][0]) <= 1e-13
+    with pytest.raises(E.PcxError, match=">= 2 host argument sets"):
+        eng.sweep_host(what, eng.make_args(sets[:1]), 2)
+
+
 def test_independent_sweep_is_bitwise_the_ordered_result(cuda_device):
     """``pcx_eval_many(PCX_EVAL_INDEPENDENT)``: evaluations declared independent are not
     ordered against each other on the device (no dependency wait, rotating scratch
