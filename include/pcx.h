@@ -325,6 +325,14 @@ int pcx_gather(pcx_engine* e, const double* in, const int64_t* perm, int64_t n,
 /* Pinned host buffers for the caller (async H2D/D2H of iterates and values). */
 int pcx_host_alloc(void** ptr, int64_t bytes);
 int pcx_host_free(void* ptr);
+/* Page-lock memory the CALLER owns (the x / lambda vectors an NLP solver hands to
+ * its callbacks -- IPOPT's TNLP::eval_* `const Number* x`, pycollo/nlp.py:40-62 --
+ * are the same few buffers for the whole solve), so that a PCX_HOST evaluation
+ * or the caller's own cudaMemcpyAsync reads them by DMA without a staging copy.
+ * PCX_ECUDA if the range cannot be registered (e.g. it already is): the buffer
+ * then simply stays pageable.                                                  */
+int pcx_host_register(void* ptr, int64_t bytes);
+int pcx_host_unregister(void* ptr);
 
 /* Number of kernel launches issued by this engine since creation, and the
  * names of the compiled kernel variants (diagnostics for bench.py).          */

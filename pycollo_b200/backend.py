@@ -590,13 +590,13 @@ class Cuda:
             (self.evaluate_H_nonzeros(x, obj_factor, lagrange), (rows, cols)),
             shape=(it.S.num_x, it.S.num_x))
 
-    def nlp_callbacks(self, ordering="cyipopt", x_check="full"):
+    def nlp_callbacks(self, ordering="cyipopt", x_check="full", register_inputs=True):
         """cyipopt-style callback object (``pycollo/nlp.py:36-76``); without
         ``hessian`` members when ``settings.derivative_level == 1``."""
         from .nlp import NlpCallbacks, NlpCallbacksFirstOrder
         cls = NlpCallbacks if int(self.ocp.settings.derivative_level) >= 2 \
             else NlpCallbacksFirstOrder
-        return cls(self._it(), ordering, x_check)
+        return cls(self._it(), ordering, x_check, register_inputs)
 
     def solve_nlp(self):
         raise NotImplementedError(

@@ -243,6 +243,7 @@ def generate(ir, phase_derivs, point_derivs, structure):
            f"#define PCX_NUM_PHASES {P}\n#define PCX_NS {NS}\n#define PCX_NB {NB}\n",
            f"#define PCX_NPOINT {npt}\n",
            f"#define PCX_NY_MAX {max([pd.NY for pd in phase_derivs] + [1])}\n",
+           f"#define PCX_NV_MAX {max([pd.NV for pd in phase_derivs] + [1])}\n",
            f"#define PCX_GS_VS 0\n#define PCX_GS_RS {NS}\n#define PCX_GS_W {2 * NS}\n"
            f"#define PCX_GS_WB {2 * NS + 1}\n",
            f"#define PCX_BV_PTVAL {structure.bv_ptval}\n#define PCX_BV_PTFN {structure.bv_ptfn}\n"

@@ -39,6 +39,12 @@
 #ifndef PCX_SCATTER_UNROLL
 #define PCX_SCATTER_UNROLL 4
 #endif
+#ifndef PCX_DECODE_V1
+#define PCX_DECODE_V1 0
+#endif
+#ifndef PCX_EARLY_WAIT
+#define PCX_EARLY_WAIT 0
+#endif
 #define PCX_STR2(x) #x
 #define PCX_STR(x) PCX_STR2(x)
 
@@ -133,6 +139,13 @@ __device__ __forceinline__ double pcx_ld_keep(const double* ptr, unsigned long l
 __device__ __forceinline__ int pcx_ld_keep(const int* ptr, unsigned long long pol) {
     int v;
     asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+
+// a load the compiler keeps where it is written (used to put the iterate in flight early)
+__device__ __forceinline__ double pcx_ld_f64(const double* ptr) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
     return v;
 }
 
@@ -389,7 +402,80 @@ struct PcxTileStatic {
     i64 o[PCX_THREADS];
     int dp[PCX_THREADS], dstep[PCX_THREADS], ostep[PCX_THREADS], cnt[PCX_THREADS];
     double cst[1 + 2 * PCX_NY_MAX];
+    // tables of the run being scattered (period offsets per variable, slot bases,
+    // section range): staged once per run so that decoding a work item needs ONE
+    // global load (its recipe word) instead of a chain of four
+    i64 run_gb[PCX_NV_MAX + 1];
+    int run_tv[PCX_NV_MAX + 2];
+    int run_lohi[2];
 };
+
+template <class Ph>
+__device__ __forceinline__ void pcx_stage_run(const PcxParams& p, const int run, const int tid,
+                                              const unsigned long long keep, PcxTileStatic& ts) {
+    const int* tv = p.type_var_off + pcx_ld_keep(p.run_type + run, keep) * (p.nvmax + 1);
+    for (int i = tid; i <= Ph::NV; i += PCX_THREADS) {
+        ts.run_tv[i] = tv[i];
+        if (i < Ph::NV) ts.run_gb[i] = pcx_ld_keep(p.run_gbase + (i64)run * p.nvmax + i, keep);
+    }
+    if (tid == 0) {
+        ts.run_lohi[0] = pcx_ld_keep(p.run_slo + run, keep);
+        ts.run_lohi[1] = pcx_ld_keep(p.run_shi + run, keep);
+    }
+}
+
+// run setup / slot decoding from the staged tables (shared memory only, apart
+// from the recipe word the caller has already fetched)
+template <class Ph>
+__device__ __forceinline__ bool pcx_run_setup_s(const PcxTileStatic& ts, const int tid,
+                                                const int* sSecOrder, PcxRun& R) {
+    constexpr int T = PCX_THREADS;
+    R.s_lo = ts.run_lohi[0];
+    R.s_hi = ts.run_lohi[1];
+    R.tv = nullptr;
+    R.rec0 = ts.run_tv[0];
+    R.Ptot = ts.run_tv[Ph::NV] - R.rec0;
+    if (R.Ptot == 0) return false;
+    R.per = 1; R.u0 = tid; R.sc0 = R.s_lo;
+    if (R.Ptot < T) {
+        R.per = T / R.Ptot;
+        const int q = tid / R.Ptot;
+        R.u0 = tid - q * R.Ptot;
+        R.sc0 = R.s_lo + q;
+        if (q >= R.per) return false;
+    }
+    R.nstep = sSecOrder[R.s_lo + 1] - 1;
+    return true;
+}
+
+template <class Ph>
+__device__ __forceinline__ bool pcx_decode_word(const unsigned long long w, const PcxRun& R,
+                                                const PcxTileStatic& ts, const double* sB,
+                                                const int* sSecNode, const int sD_off,
+                                                const int sDP_off, const int nnp, const int nsp,
+                                                PcxSlot& S) {
+    const u32 lo = (u32)w;
+    if (lo >> RC_SKIP_BIT) return false;
+    const int a = (int)((w >> RC_VAR_SHIFT) & 0xffu);
+    const int local = (int)((w >> RC_LOCAL_SHIFT) & ((1u << RC_LOCAL_BITS) - 1));
+    const int Pa = ts.run_tv[a + 1] - ts.run_tv[a];
+    const int e = lo & ((1u << RC_E_BITS) - 1);
+    const int bi = (lo >> RC_B_SHIFT) & ((1u << RC_B_BITS) - 1);
+    const int mloc = (int)((w >> RC_M_SHIFT) & ((1u << RC_M_BITS) - 1));
+    S.cc = ts.cst[(lo >> RC_C_SHIFT) & ((1u << RC_C_BITS) - 1)];
+    const bool prev = (lo >> RC_PREV_BIT) & 1u;
+    S.bcoef = sB[bi];
+    S.dp = 0; S.dstep = 0;
+    if (e) {
+        S.dp = prev ? sDP_off + (e - 1) * nsp + R.sc0
+                    : sD_off + (e - 1) * nnp + mloc + sSecNode[R.sc0 + 1];
+        S.dstep = prev ? R.per : R.per * R.nstep;
+    }
+    S.o = ts.run_gb[a] + local + (i64)(R.sc0 - R.s_lo) * Pa;
+    S.ostep = R.per * Pa;
+    S.cnt = (R.s_hi - R.sc0 + R.per - 1) / R.per;
+    return true;
+}
 
 // Staged node-diagonal Hessian entries -> global memory, one variable block at a
 // time: the block's slots of the tile's regular nodes are contiguous
@@ -480,6 +566,29 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     pcx_stamp_smid(p, tile);
 #endif
     const int nnp = nn | 1;                        // odd stride: no bank conflicts
+    // Multi-wave grids (PCX_EARLY_WAIT, chosen by the host when the tiles need three
+    // waves or more): only the first wave can overlap a previous kernel, so the
+    // dependency wait moves up here and the thread's iterate / multiplier loads are
+    // put in flight BEFORE the table chain below instead of after it -- their DRAM
+    // latency hides behind the four L2 round trips of the tables.
+    double xt0[NV > 0 ? NV : 1];
+    double lam_p[NP > 0 ? NP : 1], lam_q[NQ > 0 ? NQ : 1];     // path (this node) / integral rows
+    double xt_t0 = 0.0, xt_tF = 0.0;
+    if (PCX_EARLY_WAIT) {
+        if (!p.independent) pcx_grid_dependency_wait();
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+            xt0[a] = (tid < nn) ? pcx_ld_f64(x + xo + (i64)a * N + node0 + tid) : 0.0;
+        if (Ph::HAS_T0) xt_t0 = pcx_ld_f64(x + pb[Ph::PB_T0X]);
+        if (Ph::HAS_TF) xt_tF = pcx_ld_f64(x + pb[Ph::PB_TFX]);
+        if (WANT_H) {
+#pragma unroll
+            for (int j = 0; j < NP; ++j)
+                lam_p[j] = (tid < nn) ? pcx_ld_f64(lam + co + (i64)NY * (N - 1) + (i64)j * N + node0 + tid) : 0.0;
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) lam_q[i] = pcx_ld_f64(lam + co + (i64)NY * (N - 1) + (i64)NP * N + i);
+        }
+    }
 
     // ---- shared memory carve-up ------------------------------------------
     double* sB = reinterpret_cast<double*>(smem_raw);          // btab
@@ -572,6 +681,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
             // CTA-uniform: is there anything beyond one work item per thread?
             const int* tv0 = p.type_var_off + pcx_ld_keep(p.run_type + run0, keep) * (p.nvmax + 1);
             pre_more = (nruns > 1) || (tv0[NV] - tv0[0] > T);
+            if (pre_more && !PCX_DECODE_V1) pcx_stage_run<Ph>(p, run0, tid, keep, ts);   // visible after the next barrier
         }
     }
     // ---- the iterate and the multipliers ------------------------------------------
@@ -580,21 +690,21 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     // be complete from here on -- unless the caller declared the evaluations
     // independent (distinct buffers, rotating scratch): then consecutive kernels
     // overlap freely and their load / compute / store phases interleave
-    if (!p.independent) pcx_grid_dependency_wait();
-    PCX_STAMP(8);
-    double xt0[NV > 0 ? NV : 1];
+    if (!PCX_EARLY_WAIT) {
+        if (!p.independent) pcx_grid_dependency_wait();
+        PCX_STAMP(8);
 #pragma unroll
-    for (int a = 0; a < NV; ++a)
-        xt0[a] = (tid < nn) ? x[xo + (i64)a * N + node0 + tid] : 0.0;
-    const double xt_t0 = Ph::HAS_T0 ? x[pb[Ph::PB_T0X]] : 0.0;
-    const double xt_tF = Ph::HAS_TF ? x[pb[Ph::PB_TFX]] : 0.0;
-    double lam_p[NP > 0 ? NP : 1], lam_q[NQ > 0 ? NQ : 1];     // path (this node) / integral rows
-    if (WANT_H) {
+        for (int a = 0; a < NV; ++a)
+            xt0[a] = (tid < nn) ? x[xo + (i64)a * N + node0 + tid] : 0.0;
+        if (Ph::HAS_T0) xt_t0 = x[pb[Ph::PB_T0X]];
+        if (Ph::HAS_TF) xt_tF = x[pb[Ph::PB_TFX]];
+        if (WANT_H) {
 #pragma unroll
-        for (int j = 0; j < NP; ++j)
-            lam_p[j] = (tid < nn) ? lam[co + (i64)NY * (N - 1) + (i64)j * N + node0 + tid] : 0.0;
+            for (int j = 0; j < NP; ++j)
+                lam_p[j] = (tid < nn) ? lam[co + (i64)NY * (N - 1) + (i64)j * N + node0 + tid] : 0.0;
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) lam_q[i] = lam[co + (i64)NY * (N - 1) + (i64)NP * N + i];
+            for (int i = 0; i < NQ; ++i) lam_q[i] = lam[co + (i64)NY * (N - 1) + (i64)NP * N + i];
+        }
     }
     if (WANT_H) {
         // multipliers of the defect rows of sections k0-1 .. k1-1
@@ -820,7 +930,8 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
 
     // ---- coalesced scatter of the Jacobian values (see pcx_store_run) ----------
     if (WANT_G) {
-        // the thread's first work item was decoded in the prologue
+#if PCX_DECODE_V1
+        // (round-1 form, kept for A/B: every work item walks the table chain)
         if (sPreCnt[tid] > 0)
             pcx_store_run(out_g + sPreO[tid], sPreOstep[tid], sB + sPreDp[tid], sPreDstep[tid],
                           sPreCoef[2 * tid], sPreCoef[2 * tid + 1], sPreCnt[tid]);
@@ -839,6 +950,49 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
             }
         }
     }
+#else
+        if (!pre_more) {
+            // the thread's only work item was decoded in the prologue
+            if (sPreCnt[tid] > 0)
+                pcx_store_run(out_g + sPreO[tid], sPreOstep[tid], sB + sPreDp[tid], sPreDstep[tid],
+                              sPreCoef[2 * tid], sPreCoef[2 * tid + 1], sPreCnt[tid]);
+        } else {
+            // several work items per thread (large bodies, ragged meshes): the run's
+            // tables are staged in shared memory and the recipe word of the NEXT item
+            // is fetched before the current item's stores are issued, so the only
+            // global load of a decode is never waited for
+#pragma unroll 1
+            for (int r = 0; r < nruns; ++r) {
+                if (r > 0) {
+                    __syncthreads();
+                    pcx_stage_run<Ph>(p, run0 + r, tid, keep, ts);
+                    __syncthreads();
+                }
+                PcxRun run;
+                const bool ok = pcx_run_setup_s<Ph>(ts, tid, sSecOrder, run);
+                int u = run.u0 + (r == 0 ? T : 0);       // run0's first item: pre-decoded
+                bool have = ok && u < run.Ptot;
+                unsigned long long w = have ? pcx_ld_keep(p.recipes + run.rec0 + u, keep) : 0ull;
+                if (r == 0 && sPreCnt[tid] > 0)
+                    pcx_store_run(out_g + sPreO[tid], sPreOstep[tid], sB + sPreDp[tid],
+                                  sPreDstep[tid], sPreCoef[2 * tid], sPreCoef[2 * tid + 1],
+                                  sPreCnt[tid]);
+                while (have) {
+                    const int un = u + T;
+                    const bool more = (run.Ptot >= T) && (un < run.Ptot);
+                    const unsigned long long wn =
+                        more ? pcx_ld_keep(p.recipes + run.rec0 + un, keep) : 0ull;
+                    PcxSlot sl;
+                    if (pcx_decode_word<Ph>(w, run, ts, sB, sSecNode, (int)(sD - sB),
+                                            (int)(sDP - sB), nnp, nsp, sl))
+                        pcx_store_run(out_g + sl.o, sl.ostep, sB + sl.dp, sl.dstep, sl.bcoef,
+                                      sl.cc, sl.cnt);
+                    w = wn; u = un; have = more;
+                }
+            }
+        }
+    }
+#endif
 
     PCX_STAMP(3);
 }

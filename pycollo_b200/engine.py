@@ -89,6 +89,8 @@ def load_library(rebuild=False):
     lib.pcx_gather.argtypes = [vp, dp, dp, i64, dp, i32, vp]
     lib.pcx_host_alloc.argtypes = [ctypes.POINTER(vp), i64]
     lib.pcx_host_free.argtypes = [vp]
+    lib.pcx_host_register.argtypes = [vp, i64]
+    lib.pcx_host_unregister.argtypes = [vp]
     lib.pcx_launch_count.argtypes = [vp]
     lib.pcx_launch_count.restype = i64
     lib.pcx_last_d2h_bytes.argtypes = [vp]

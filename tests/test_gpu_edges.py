@@ -212,6 +212,50 @@ def test_cyipopt_adapter_orderings_and_staging():
         ocp1._backend.evaluate_H_nonzeros(x1, 1.0, None)
 
 
+def test_cyipopt_adapter_uploads_from_the_callers_arrays():
+    """``register_inputs``: the caller's x / multiplier arrays are page-locked on first
+    sight and become the DMA source (no staging copy).  Results equal the staging
+    path's bit for bit; an array modified IN PLACE and flagged new is read again."""
+    from pycollo_b200.nlp import NlpCallbacks
+    ocp = examples.cart_pole_swing_up()
+    examples.set_mesh(ocp, 3000, 4)
+    ocp.initialise()
+    it = ocp._backend.current_iteration
+    rng = np.random.default_rng(2)
+    x = it.guess_x_tilde + 0.05 * rng.standard_normal(it.num_x)
+    lam = rng.standard_normal(it.num_c)
+    assert x.nbytes >= (1 << 16)
+    reg = NlpCallbacks(it, "cyipopt", register_inputs=True)
+    stg = NlpCallbacks(it, "cyipopt", register_inputs=False)
+    for rnd in range(3):
+        f = reg.objective(x, new_x=True)
+        assert f == stg.objective(x, new_x=True)
+        assert np.array_equal(reg.gradient(x, new_x=False), stg.gradient(x, new_x=False))
+        assert np.array_equal(reg.constraints(x, new_x=False), stg.constraints(x, new_x=False))
+        assert np.array_equal(reg.jacobian(x, new_x=False), stg.jacobian(x, new_x=False))
+        assert np.array_equal(reg.hessian(x, lam, 0.7, new_x=False),
+                              stg.hessian(x, lam, 0.7, new_x=False))
+        x += 0.01 * rng.standard_normal(it.num_x)        # same address, new values
+        lam *= 1.1
+    assert reg.num_registered_uploads == 3 and stg.num_registered_uploads == 0
+    assert len(reg._registered) == 2                     # x and lam, registered once each
+    reg.close()
+    assert not reg._registered
+    # the sampled compare works without this object's own copy of x
+    smp = NlpCallbacks(it, "cyipopt", x_check="sampled")
+    j0 = smp.jacobian(x).copy()
+    up = smp.num_x_uploads
+    smp.objective(x)
+    assert smp.num_x_uploads == up and smp.num_registered_uploads == 1
+    x[::max(1, x.size // 4096)] += 1e-3
+    assert not np.array_equal(smp.jacobian(x), j0) and smp.num_x_uploads == up + 1
+    # a non-contiguous / converted input is a temporary: staged, never registered
+    n0 = len(smp._registered)
+    smp.objective(x.astype(np.float32))
+    assert len(smp._registered) == n0
+    smp.close()
+
+
 @pytest.mark.parametrize("name,K,nodes,kw", [
     ("cart_pole_swing_up", 700, 4, {}),
     ("double_pendulum", 6, [4, 7, 2, 10, 3, 5], dict(max_tile_nodes=20)),

@@ -27,9 +27,10 @@ def iterate(cb, x, flag):
     cb.jacobian(x, **kw(False)); cb.hessian(x, lam, 1.0, **kw(False))
 
 
-for ordering, x_check, flag in (("cyipopt", "full", None), ("cyipopt", "sampled", None),
-                                ("cyipopt", "full", True), ("casadi", "full", True)):
-    cb = NlpCallbacks(it, ordering, x_check)
+for ordering, x_check, flag, reg in (("cyipopt", "full", None, True), ("cyipopt", "sampled", None, True),
+                                     ("cyipopt", "full", True, False), ("cyipopt", "full", True, True),
+                                     ("casadi", "full", True, True)):
+    cb = NlpCallbacks(it, ordering, x_check, register_inputs=reg)
     for k in range(3):
         iterate(cb, xs[k % 4], flag)
     n = 30
@@ -39,5 +40,8 @@ for ordering, x_check, flag in (("cyipopt", "full", None), ("cyipopt", "sampled"
     dt = (time.perf_counter() - t0) / n
     print(json.dumps(dict(adapter="NlpCallbacks", ordering=ordering,
                           same_x_test=("new_x flag" if flag else x_check), nodes=100000,
+                          upload=("DMA from the caller's arrays (registered once)"
+                                  if cb.num_registered_uploads else "staging copy"),
                           callbacks_per_iterate=5, x_uploads_per_iterate=cb.num_x_uploads / (n + 3),
                           ms_per_iterate=round(1e3 * dt, 3), iterates_per_s=round(1 / dt, 1))), flush=True)
+    cb.close()

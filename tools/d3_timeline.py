@@ -1,0 +1,54 @@
+"""Per-CTA phase durations of the fused G+H kernel on Delta III (config 4, multi-wave grid):
+where a tile's lifetime goes -- table prologue, input loads, node phase, scatter.
+python tools/d3_timeline.py [K]      (extra NVRTC options via PCX_NVRTC_EXTRA are kept)"""
+import ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["PCX_NVRTC_EXTRA"] = (os.environ.get("PCX_NVRTC_EXTRA", "") + " -DPCX_DEBUG_TIMELINE").strip()
+import numpy as np, torch
+from examples import problems
+from examples.cases import lower_case
+from pycollo_b200 import engine as E
+
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 83333
+low, _, scal = lower_case(problems.delta_iii_launch_vehicle(), "lobatto", K, 4, seed=0)
+S = low.S
+eng = E.Engine(S, low.layouts, low.header, structure=False)
+eng.set_scaling(*scal)
+dev = torch.device("cuda")
+g = torch.Generator(device=dev).manual_seed(0)
+x = 0.1 + 0.3 * torch.rand(S.num_x, dtype=torch.float64, device=dev, generator=g)
+lam = torch.randn(S.num_c, dtype=torch.float64, device=dev, generator=g)
+jac = torch.empty(S.nnz_g, dtype=torch.float64, device=dev)
+hes = torch.empty(S.nnz_h, dtype=torch.float64, device=dev)
+st = torch.cuda.current_stream().cuda_stream
+what = E.EVAL_JAC | E.EVAL_HESS
+for _ in range(3):
+    eng.eval_ptr(what, x, lam=lam, jac=jac, hess=hes, stream=st)
+torch.cuda.synchronize()
+buf = np.zeros(S.num_tiles * 16)
+eng.lib.pcx_debug_read_partials.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+eng.lib.pcx_debug_read_partials(eng.h, buf.ctypes.data_as(ctypes.c_void_p), buf.size)
+t = buf.reshape(-1, 16)
+t = np.where(t == 0, np.nan, t)
+t0 = np.nanmin(t[:, 0])
+us = (t - t0) / 1e3
+print("Delta III, tiles", S.num_tiles, "threads", S.threads, "opts", os.environ["PCX_NVRTC_EXTRA"])
+print("kernel span %.1f us" % np.nanmax(us[:, 5]))
+
+
+def stat(name, a):
+    a = a[~np.isnan(a)]
+    print(f"{name:34s} med {np.median(a):6.2f}  p10 {np.percentile(a,10):6.2f}  p90 {np.percentile(a,90):6.2f} us")
+
+
+stat("CTA lifetime", us[:, 5] - us[:, 0])
+stat("start -> tile descriptor known", us[:, 7] - us[:, 0])
+stat("descriptor -> inputs in smem", us[:, 1] - us[:, 7])
+stat("node phase (generated body)", us[:, 2] - us[:, 1])
+stat("signal + rows + scatter of G", us[:, 3] - us[:, 2])
+w = us[:, 11:15]
+stat("intra-CTA warp skew, node phase", np.nanmax(w, axis=1) - np.nanmin(w, axis=1))
+smid = np.nan_to_num(t[:, 10]).astype(int)
+cnt = np.bincount(smid)
+print("CTAs per SM: min %d max %d" % (cnt[cnt > 0].min(), cnt.max()))
