@@ -318,6 +318,8 @@ def _phase_struct(q, ph, pd, lay, NS):
     stage_h = stage_h_rule(len(pd.h2vv))
     s.append(f"    static constexpr bool STAGE_H = {'true' if stage_h else 'false'};\n")
     s.append(f"    static constexpr int HP = {(len(pd.h2vv) | 1) if stage_h else 0};\n")
+    # stride of a node's row of staged node-diagonal entries in the two-pass node phase
+    s.append(f"    static constexpr int HPS = {len(pd.h2vv) | 1};\n")
     s.append(_cfun("HB_OFF", hb_off))
 
     # ---- the expression body ----

@@ -39,11 +39,36 @@
 #ifndef PCX_SCATTER_UNROLL
 #define PCX_SCATTER_UNROLL 4
 #endif
+// Two-pass node phase for large bodies (fused G+H launches): pass 1 evaluates the
+// first-derivative outputs, the Jacobian is scattered, then pass 2 evaluates the
+// second-derivative outputs INTO THE SHARED MEMORY THE STAGED FIRST DERIVATIVES
+// JUST VACATED and the Hessian entries leave as full sectors.  Written directly
+// (one 8-byte piece of a different sector per lane) the Hessian stores cost as many
+// SM->L2 sector slots as the whole Jacobian (profiles/r02_d3_knockout.txt).
+#ifndef PCX_TWO_PASS
+#define PCX_TWO_PASS 0
+#endif
+// timing experiments only (wrong results): keep the arithmetic, drop the stores
+#ifndef PCX_KO_HST
+#define PCX_KO_HST 0
+#endif
+#ifndef PCX_KO_GST
+#define PCX_KO_GST 0
+#endif
+__device__ double pcx_ko_sink;
 #ifndef PCX_DECODE_V1
 #define PCX_DECODE_V1 0
 #endif
 #ifndef PCX_EARLY_WAIT
 #define PCX_EARLY_WAIT 0
+#endif
+// the thread's first scatter work item decoded from the STAGED run tables (one
+// dependent global load instead of four); needs the staged decode
+#ifndef PCX_PRE_STAGED
+#define PCX_PRE_STAGED 0
+#endif
+#if PCX_PRE_STAGED && PCX_DECODE_V1
+#error "PCX_PRE_STAGED needs the staged decode (PCX_DECODE_V1=0)"
 #endif
 #define PCX_STR2(x) #x
 #define PCX_STR(x) PCX_STR2(x)
@@ -243,6 +268,13 @@ __device__ __forceinline__ bool pcx_decode_slot(const PcxParams& p, const int ru
 __device__ __forceinline__ void pcx_store_run(double* o, const int ostep, const double* dp,
                                               const int dstep, const double bcoef,
                                               const double cc, const int cnt) {
+#if PCX_KO_GST
+    double acc = 0.0;
+    _Pragma(PCX_STR(unroll PCX_SCATTER_UNROLL))
+    for (int it = 0; it < cnt; ++it) { acc += bcoef * (*dp) + cc; dp += dstep; }
+    if (acc == 1.2345e-300) *o = acc;
+    return;
+#endif
     _Pragma(PCX_STR(unroll PCX_SCATTER_UNROLL))
     for (int it = 0; it < cnt; ++it) {
         *o = bcoef * (*dp) + cc;
@@ -256,9 +288,12 @@ __device__ __forceinline__ void pcx_store_run(double* o, const int ostep, const 
 // live after it has been produced (a problem like the Delta III launcher has
 // ~90 results per node; held in arrays they alone overflow the register file).
 // ---------------------------------------------------------------------------
-template <class Ph>
+template <class Ph, int MODE = 0>      // 0: every output, 1: first derivatives only, 2: second only
 struct PcxNodeSink {
     static constexpr int F_ = PCX_FLAGS;
+    static constexpr bool FIRST = MODE != 2, SECOND = MODE != 1;
+    static constexpr bool STG_H = Ph::STAGE_H || MODE == 2;
+    static constexpr int HSTR = MODE == 2 ? Ph::HPS : Ph::HP;
     static constexpr bool WANT_C = (F_ & PCX_F_C) != 0, WANT_DY = (F_ & PCX_F_DY) != 0;
     static constexpr bool WANT_G = (F_ & PCX_F_G) != 0, WANT_H = (F_ & PCX_F_H) != 0;
     static constexpr bool HAS_T = Ph::HAS_T0 || Ph::HAS_TF;
@@ -268,6 +303,7 @@ struct PcxNodeSink {
     const double* ps; const i64* pb;
     double *sF, *sD, *sDS, *sDP;          // already offset by the node / section
     double* sH;                           // this node's row of staged Hessian entries
+    int hrow;                             // (two-pass form) index among the tile's regular nodes
     int nnp, nsp;
     bool sec_start, owned, regular;
     double hp, wq, h_k, h_pr;
@@ -282,6 +318,7 @@ struct PcxNodeSink {
     }
 
     template <int I> __device__ __forceinline__ void F(const double val) const {
+        if (!FIRST) return;
         if (I < NY) {
             if (NEED_SF) sF[I * nnp] = val;
             if (WANT_DY && owned) out_dy[(i64)I * N] = val;
@@ -298,7 +335,7 @@ struct PcxNodeSink {
     // a section's first node, h_{k-1} for the rows of the previous section
     // (second copy, one slot per section)
     template <int K> __device__ __forceinline__ void D1V(const double val) const {
-        if (!WANT_G) return;
+        if (!WANT_G || !FIRST) return;
         constexpr int fam = Ph::FAM(Ph::D1V_FN(K));
         const double fac = fam == 0 ? hp : (fam == 1 ? 1.0 : -hp * wq);
         const double d = ps[Ph::OFF_D1V + K] * fac * val;
@@ -306,7 +343,7 @@ struct PcxNodeSink {
         if (fam == 0 && sec_start) sDP[K * nsp] = d * h_pr;
     }
     template <int K> __device__ __forceinline__ void D1S(const double val) const {
-        if (!WANT_G) return;
+        if (!WANT_G || !FIRST) return;
         constexpr int fam = Ph::FAM(Ph::D1S_FN(K));
         if (fam == 0) {
             sDS[d1s_rank(K, 0) * nnp] = ps[Ph::OFF_D1S + K] * hp * val;
@@ -317,9 +354,15 @@ struct PcxNodeSink {
         }
     }
     template <int K> __device__ __forceinline__ void H2VV(const double val) const {
-        if (!WANT_H || !owned) return;
+        if (!WANT_H || !SECOND || !owned) return;
+        if (PCX_KO_HST) { if (ps[Ph::OFF_H2VV + K] * val == 1.2345e-300) pcx_ko_sink = val; return; }
         if (regular) {
-            if (Ph::STAGE_H)
+            if (MODE == 2)
+                // output order: block b of the tile's regular nodes is one contiguous
+                // run of NA(b) entries per node -- the flush is a straight copy
+                sH[Ph::HB_OFF(Ph::H2VV_B(K)) * PCX_THREADS + hrow * Ph::NA(Ph::H2VV_B(K))
+                   + Ph::H2VV_POS(K)] = ps[Ph::OFF_H2VV + K] * val;
+            else if (STG_H)
                 sH[Ph::HB_OFF(Ph::H2VV_B(K)) + Ph::H2VV_POS(K)] = ps[Ph::OFF_H2VV + K] * val;
             else
                 out_h[pb[Ph::PB_HREG + Ph::H2VV_B(K)] + (m - 1) * Ph::NA(Ph::H2VV_B(K))
@@ -329,7 +372,7 @@ struct PcxNodeSink {
         }
     }
     template <int K> __device__ __forceinline__ void H2VS(const double val) const {
-        if (!WANT_H || !owned) return;
+        if (!WANT_H || !SECOND || !owned) return;
         if (regular) out_h[pb[Ph::PB_HS + K] + (m - 1)] = ps[Ph::OFF_H2VS + K] * val;
         else irr[Ph::NH2VV + K] = val;
     }
@@ -337,7 +380,7 @@ struct PcxNodeSink {
         // rows of H against t0 / tF exist only for free times; with both times
         // fixed nothing consumes these results and the compiler drops their
         // computation (and the t-multipliers feeding it) from the body
-        if (!WANT_H || !HAS_T || !owned) return;
+        if (!WANT_H || !SECOND || !HAS_T || !owned) return;
         if (regular) {
             if (Ph::HAS_T0) out_h[pb[Ph::PB_HT0 + K] + (m - 1)] = ps[Ph::OFF_HT0 + K] * val;
             if (Ph::HAS_TF) out_h[pb[Ph::PB_HTF + K] + (m - 1)] = ps[Ph::OFF_HTF + K] * val;
@@ -346,10 +389,10 @@ struct PcxNodeSink {
         }
     }
     template <int K> __device__ __forceinline__ void HTS(const double val) const {
-        if (WANT_H && owned) red[Ph::RED_HTS + K] += val;
+        if (WANT_H && SECOND && owned) red[Ph::RED_HTS + K] += val;
     }
     template <int K> __device__ __forceinline__ void H2SS(const double val) const {
-        if (WANT_H && owned) red[Ph::RED_HSS + K] += val;
+        if (WANT_H && SECOND && owned) red[Ph::RED_HSS + K] += val;
     }
 };
 
@@ -480,7 +523,7 @@ __device__ __forceinline__ bool pcx_decode_word(const unsigned long long w, cons
 // Staged node-diagonal Hessian entries -> global memory, one variable block at a
 // time: the block's slots of the tile's regular nodes are contiguous
 // (NA(b) per node), consecutive threads write consecutive doubles.
-template <class Ph, int... Bs>
+template <class Ph, int HSTR, int... Bs>
 __device__ __forceinline__ void pcx_flush_h(const double* sH, double* out_h, const i64* pb,
                                             const i64 m_first, const int a0, const int n_reg,
                                             const int tid, PcxSeq<Bs...>) {
@@ -489,11 +532,29 @@ __device__ __forceinline__ void pcx_flush_h(const double* sH, double* out_h, con
         constexpr int NAb = Ph::NA(Bs);
         if (NAb > 0) {
             double* dst = out_h + pb[Ph::PB_HREG + Bs] + (m_first - 1) * NAb;
-            const double* src = sH + a0 * Ph::HP + Ph::HB_OFF(Bs);
+            const double* src = sH + a0 * HSTR + Ph::HB_OFF(Bs);
             for (int i = tid; i < n_reg * NAb; i += T) {
                 const int nd = i / NAb;
-                dst[i] = src[nd * Ph::HP + (i - nd * NAb)];
+                dst[i] = src[nd * HSTR + (i - nd * NAb)];
             }
+        }
+    }(), 0)...};
+    (void)dummy;
+}
+
+// two-pass form: the entries were staged in output order, block b at sH + HB_OFF(b) * T
+template <class Ph, int... Bs>
+__device__ __forceinline__ void pcx_copy_h(const double* sH, double* out_h, const i64* pb,
+                                           const i64 m_first, const int n_reg, const int tid,
+                                           PcxSeq<Bs...>) {
+    constexpr int T = PCX_THREADS;
+    int dummy[] = {0, ([&] {
+        constexpr int NAb = Ph::NA(Bs);
+        if (NAb > 0) {
+            double* dst = out_h + pb[Ph::PB_HREG + Bs] + (m_first - 1) * NAb;
+            const double* src = sH + Ph::HB_OFF(Bs) * T;
+#pragma unroll 4
+            for (int i = tid; i < n_reg * NAb; i += T) dst[i] = src[i];
         }
     }(), 0)...};
     (void)dummy;
@@ -516,6 +577,11 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     constexpr bool NEED_SF = WANT_C || (WANT_G && HAS_T);
     constexpr int NDS = Ph::ND1SD;                 // d-family s-derivative entries
     constexpr bool NEED_ROWS = NEED_SF || (WANT_G && NDS > 0);
+    constexpr int NOUT = NF + Ph::ND1V + Ph::ND1S + Ph::NH2VV + Ph::NH2VS + Ph::NH2SS
+                         + Ph::NHTV + Ph::NHTS;
+    constexpr bool PARK = NOUT <= 40;              // small bodies: results parked in registers
+    constexpr bool TWO = (PCX_TWO_PASS != 0) && WANT_G && WANT_H && !PARK && Ph::NH2VV > 0
+                         && !Ph::STAGE_H;
 
     const int tid = threadIdx.x;
     PCX_STAMP(0);
@@ -602,6 +668,9 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     const int lam_stride = nn + PCX_LAM_HALO;
     double* sH = sLam + (WANT_H ? NY * lam_stride : 0);        // HP * nn (staged H entries)
     double* sRed = sH + ((WANT_H && Ph::STAGE_H) ? Ph::HP * nn : 0);   // T/32
+    // two-pass node phase: the second pass stages NH2VV * T Hessian entries over
+    // sD / sDP / sDS / sLam, all dead once the Jacobian has been scattered
+    if (TWO && sD + Ph::NH2VV * T > sRed) sRed = sD + Ph::NH2VV * T;
     int* sSecNode = reinterpret_cast<int*>(sRed + T / 32);     // nsec+2 (prev first)
     int* sSecOrder = sSecNode + (nsec + 2);                    // nsec+1 (prev first)
     int* sNodeSec = sSecOrder + (nsec + 1);                    // nn
@@ -633,6 +702,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         sWoff[s] = p.order_w_off[ord];
     }
     if (tid == 0) sSecNode[nsec + 1] = nn - 1;
+    if (WANT_G && PCX_PRE_STAGED && nruns > 0) pcx_stage_run<Ph>(p, run0, tid, keep, ts);
     __syncthreads();
     for (int s = tid; s < nsec; s += T) {
         const int b = sSecNode[s + 1], n = sSecOrder[s + 1];
@@ -665,7 +735,25 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     // a chain of dependent loads: walked here, in the shadow of the previous
     // kernel, instead of between the node phase and the first store
     bool pre_more = false;
-    if (WANT_G) {
+    if (WANT_G && PCX_PRE_STAGED) {
+        // the first run's tables were staged with the section table (before the first
+        // barrier): the decode is ONE global load (the recipe word) + shared memory
+        sPreCnt[tid] = 0;
+        if (nruns > 0) {
+            PcxRun run;
+            if (pcx_run_setup_s<Ph>(ts, tid, sSecOrder, run)) {
+                const unsigned long long w = pcx_ld_keep(p.recipes + run.rec0 + run.u0, keep);
+                PcxSlot sl;
+                if (pcx_decode_word<Ph>(w, run, ts, sB, sSecNode, (int)(sD - sB), (int)(sDP - sB),
+                                        nnp, nsp, sl)) {
+                    sPreCoef[2 * tid] = sl.bcoef; sPreCoef[2 * tid + 1] = sl.cc;
+                    sPreO[tid] = sl.o; sPreDp[tid] = sl.dp; sPreDstep[tid] = sl.dstep;
+                    sPreOstep[tid] = sl.ostep; sPreCnt[tid] = sl.cnt;
+                }
+            }
+            pre_more = (nruns > 1) || (ts.run_tv[NV] - ts.run_tv[0] > T);
+        }
+    } else if (WANT_G) {
         sPreCnt[tid] = 0;
         if (nruns > 0) {
             PcxRun run;
@@ -740,18 +828,32 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     double* bv = p.bv + (i64)inst * p.bv_size;
 
     // ---- node-parallel evaluation ---------------------------------------------
+    // (declared at function scope: the two-pass form evaluates the body a second time
+    // after the Jacobian scatter, from the same unscaled variables and multipliers)
+    double v[NV + NS > 0 ? NV + NS : 1];
+    double muh[NF > 0 ? NF : 1], mut[NF > 0 ? NF : 1];
+    const bool owned = active && ((ml < nn - 1) || last_tile);
+    const i64 m = node0 + ml;
+#define PCX_SINK_SETUP(SK)                                                                   \
+    SK.ps = ps; SK.pb = pb;                                                                   \
+    SK.sF = sF + ml; SK.sD = sD + ml; SK.sDS = sDS + ml; SK.sDP = sDP + s;                    \
+    SK.sH = sH + ml * Ph::HP;                                                                 \
+    SK.nnp = nnp; SK.nsp = nsp; SK.sec_start = (mloc == 0);                                   \
+    SK.hp = hp; SK.wq = wq; SK.h_k = h_k; SK.h_pr = h_pr;                                     \
+    SK.owned = owned; SK.regular = (m != 0) && (m != N - 1);                                  \
+    SK.m = m; SK.N = N;                                                                       \
+    SK.out_c_path = WANT_C ? out_c + co + (i64)NY * (N - 1) + m : nullptr;                    \
+    SK.out_dy = WANT_DY ? out_dy + pb[Ph::PB_DYOFF] + m : nullptr;                            \
+    SK.out_g = out_g; SK.out_h = out_h;                                                       \
+    SK.irr = bv + pb[m == 0 ? Ph::PB_IRR0 : Ph::PB_IRR1];                                     \
+    SK.red = red;
     if (active) {
-        const bool owned = (ml < nn - 1) || last_tile;
-        const i64 m = node0 + ml;
-
-        double v[NV + NS > 0 ? NV + NS : 1];
 #pragma unroll
         for (int a = 0; a < NV; ++a)
             v[a] = pcx_unscale(ps[Ph::OFF_VV + a], xt0[a], ps[Ph::OFF_RV + a]);
 #pragma unroll
         for (int j = 0; j < NS; ++j) v[NV + j] = sv[j];
 
-        double muh[NF > 0 ? NF : 1], mut[NF > 0 ? NF : 1];
 #pragma unroll
         for (int e = 0; e < NF; ++e) { muh[e] = 0.0; mut[e] = 0.0; }
         if (WANT_H) {
@@ -799,25 +901,11 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
 
         // the generated body hands every result to the sink the moment it
         // exists: staged (G), stored (H, dy, path rows of c) or accumulated
-        constexpr int NOUT = NF + Ph::ND1V + Ph::ND1S + Ph::NH2VV + Ph::NH2VS + Ph::NH2SS
-                             + Ph::NHTV + Ph::NHTS;
-        constexpr bool PARK = NOUT <= 40;
-        PcxParkingSink<Ph> parked;
-        if (PARK) Ph::eval(v, muh, mut, parked);
-        PcxNodeSink<Ph> sink;
-        sink.ps = ps; sink.pb = pb;
-        sink.sF = sF + ml; sink.sD = sD + ml; sink.sDS = sDS + ml; sink.sDP = sDP + s;
-        sink.sH = sH + ml * Ph::HP;
-        sink.nnp = nnp; sink.nsp = nsp; sink.sec_start = (mloc == 0);
-        sink.hp = hp; sink.wq = wq; sink.h_k = h_k; sink.h_pr = h_pr;
-        sink.owned = owned; sink.regular = (m != 0) && (m != N - 1);
-        sink.m = m; sink.N = N;
-        sink.out_c_path = WANT_C ? out_c + co + (i64)NY * (N - 1) + m : nullptr;
-        sink.out_dy = WANT_DY ? out_dy + pb[Ph::PB_DYOFF] + m : nullptr;
-        sink.out_g = out_g; sink.out_h = out_h;
-        sink.irr = bv + pb[m == 0 ? Ph::PB_IRR0 : Ph::PB_IRR1];
-        sink.red = red;
         if (PARK) {
+            PcxParkingSink<Ph> parked;
+            Ph::eval(v, muh, mut, parked);
+            PcxNodeSink<Ph> sink;
+            PCX_SINK_SETUP(sink)
             pcx_drain_F(parked, sink, typename PcxMakeSeq<NF>::type());
             pcx_drain_D1V(parked, sink, typename PcxMakeSeq<Ph::ND1V>::type());
             pcx_drain_D1S(parked, sink, typename PcxMakeSeq<Ph::ND1S>::type());
@@ -826,7 +914,13 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
             pcx_drain_H2SS(parked, sink, typename PcxMakeSeq<Ph::NH2SS>::type());
             pcx_drain_HTV(parked, sink, typename PcxMakeSeq<Ph::NHTV>::type());
             pcx_drain_HTS(parked, sink, typename PcxMakeSeq<Ph::NHTS>::type());
+        } else if (TWO) {
+            PcxNodeSink<Ph, 1> sink;                 // first pass: f, first derivatives
+            PCX_SINK_SETUP(sink)
+            Ph::eval(v, muh, mut, sink);
         } else {
+            PcxNodeSink<Ph> sink;
+            PCX_SINK_SETUP(sink)
             Ph::eval(v, muh, mut, sink);
         }
         if (WANT_GRAD && owned) {
@@ -854,32 +948,35 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     // zeroed gradient entries) exists once the node phase is over: signalling
     // here, before the bulk of the value stores is issued, keeps the fence
     // (which waits for the CTA's outstanding stores) short.
-    if (pcx_need_red<Ph>()) {
-#pragma unroll
-        for (int k = 0; k < Ph::NRED; ++k) {
-            const double r = pcx_block_sum(red[k], sRed);
-            if (tid == 0)
-                p.partials[((i64)inst * p.num_tiles + tile) * p.nred_max + k] = r;
+    auto signal_border = [&]() {
+        if (pcx_need_red<Ph>()) {
+    #pragma unroll
+            for (int k = 0; k < Ph::NRED; ++k) {
+                const double r = pcx_block_sum(red[k], sRed);
+                if (tid == 0)
+                    p.partials[((i64)inst * p.num_tiles + tile) * p.nred_max + k] = r;
+            }
         }
-    }
-    if (pcx_need_red<Ph>() || (WANT_H && (k0 == 0 || last_tile))
-        || (WANT_GRAD && (k0 == 0 || last_tile || tile == 0))) {
-        // only the threads that wrote something the border pass reads fence: thread 0
-        // (reduction partials), the threads of the phase's two end nodes (their
-        // Hessian entries) and, with GRAD, every thread (zeroed gradient entries).
-        // A fence waits for the calling thread's outstanding stores -- for a large
-        // body that is ~40 direct Hessian stores per node, and a CTA-wide fence made
-        // the signalling tiles twice as slow as the others.
-        const i64 m_me = node0 + tid;
-        if (WANT_GRAD || tid == 0 || (active && (m_me == 0 || m_me == N - 1))) __threadfence();
-        __syncthreads();
-        if (tid == 0) atomicAdd(p.ticket + inst, 1u);
-    }
+        if (pcx_need_red<Ph>() || (WANT_H && (k0 == 0 || last_tile))
+            || (WANT_GRAD && (k0 == 0 || last_tile || tile == 0))) {
+            // only the threads that wrote something the border pass reads fence: thread 0
+            // (reduction partials), the threads of the phase's two end nodes (their
+            // Hessian entries) and, with GRAD, every thread (zeroed gradient entries).
+            // A fence waits for the calling thread's outstanding stores -- for a large
+            // body that is ~40 direct Hessian stores per node, and a CTA-wide fence made
+            // the signalling tiles twice as slow as the others.
+            const i64 m_me = node0 + tid;
+            if (WANT_GRAD || tid == 0 || (active && (m_me == 0 || m_me == N - 1))) __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicAdd(p.ticket + inst, 1u);
+        }
+    };
+    if (!TWO) signal_border();
     // ---- staged Hessian entries of the tile's regular nodes, block by block ------
     if (WANT_H && Ph::STAGE_H) {
         const int a0 = (node0 == 0) ? 1 : 0;               // node 0 / N-1 go through irr
-        pcx_flush_h<Ph>(sH, out_h, pb, node0 + a0, a0, (nn - 1) - a0, tid,
-                        typename PcxMakeSeq<NV>::type());
+        pcx_flush_h<Ph, Ph::HP>(sH, out_h, pb, node0 + a0, a0, (nn - 1) - a0, tid,
+                                typename PcxMakeSeq<NV>::type());
     }
     // ---- row-oriented contractions: defect rows of c, t/s columns of G -------
     if (NEED_ROWS) {
@@ -993,6 +1090,26 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         }
     }
 #endif
+
+    // ---- second pass of the two-pass node phase ----------------------------------
+    if (TWO) {
+        __syncthreads();                 // the staged first derivatives have been consumed
+        PCX_STAMP(4);
+        if (active) {
+            PcxNodeSink<Ph, 2> sink;     // second derivatives only; the compiler drops the rest
+            PCX_SINK_SETUP(sink)
+            sink.sH = sD;
+            sink.hrow = ml - ((node0 == 0) ? 1 : 0);
+            Ph::eval(v, muh, mut, sink);
+        }
+        __syncthreads();
+        PCX_STAMP(15);
+        signal_border();
+        const int a0 = (node0 == 0) ? 1 : 0;               // node 0 / N-1 go through irr
+        pcx_copy_h<Ph>(sD, out_h, pb, node0 + a0, (nn - 1) - a0, tid,
+                       typename PcxMakeSeq<NV>::type());
+    }
+#undef PCX_SINK_SETUP
 
     PCX_STAMP(3);
 }

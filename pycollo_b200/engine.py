@@ -288,9 +288,17 @@ def smem_bytes(S, layouts, threads):
         nds = sum(1 for e, _ in pd.d1s if pd.fam[e] == "d")
         from .codegen import stage_h_rule
         hp = (len(pd.h2vv) | 1) if stage_h_rule(len(pd.h2vv)) else 0
+        # two-pass node phase (large bodies): the second pass stages NH2VV * threads
+        # Hessian entries over sD / sDP / sDS / sLam; room beyond them only if they are smaller
+        nout = (len(pd.fns) + len(pd.d1v) + len(pd.d1s) + len(pd.h2vv) + len(pd.h2vs)
+                + len(pd.h2ss) + len(pd.htv) + len(pd.hts))
+        two_extra = 0
+        if nout > 40 and len(pd.h2vv) > 0 and not hp:
+            region = (len(pd.d1v) + nds) * (NN | 1) + len(pd.d1v) * (SS + 1) + pd.NY * (NN + 24)
+            two_extra = max(0, len(pd.h2vv) * threads - region)
         dbl = (len(S.btab) + SS + 1 + (pd.NY + len(pd.d1v) + nds) * (NN | 1)
                + len(pd.d1v) * (SS + 1)
-               + pd.NY * (NN + 24) + hp * NN + threads // 32 + 2)      # PCX_LAM_HALO
+               + pd.NY * (NN + 24) + hp * NN + two_extra + threads // 32 + 2)      # PCX_LAM_HALO
         ints = (SS + 2) + (SS + 1) + NN + 2 * (SS + 1) + 8
         best = max(best, 8 * dbl + 4 * ints)
     best = max(best, 8 * (32 + S.bv_size))      # border pass: scratch + BV

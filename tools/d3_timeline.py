@@ -46,7 +46,12 @@ stat("CTA lifetime", us[:, 5] - us[:, 0])
 stat("start -> tile descriptor known", us[:, 7] - us[:, 0])
 stat("descriptor -> inputs in smem", us[:, 1] - us[:, 7])
 stat("node phase (generated body)", us[:, 2] - us[:, 1])
-stat("signal + rows + scatter of G", us[:, 3] - us[:, 2])
+if np.isnan(us[:, 4]).all():
+    stat("signal + rows + scatter of G", us[:, 3] - us[:, 2])
+else:                                           # two-pass form
+    stat("rows + scatter of G", us[:, 4] - us[:, 2])
+    stat("second pass (Hessian body)", us[:, 15] - us[:, 4])
+    stat("signal + copy of H", us[:, 3] - us[:, 15])
 w = us[:, 11:15]
 stat("intra-CTA warp skew, node phase", np.nanmax(w, axis=1) - np.nanmin(w, axis=1))
 smid = np.nan_to_num(t[:, 10]).astype(int)
