@@ -45,8 +45,20 @@
 // JUST VACATED and the Hessian entries leave as full sectors.  Written directly
 // (one 8-byte piece of a different sector per lane) the Hessian stores cost as many
 // SM->L2 sector slots as the whole Jacobian (profiles/r02_d3_knockout.txt).
+// On by default for bodies with at least PCX_TWO_PASS_MIN node-diagonal Hessian
+// entries per node (Delta III 37: 0.468 -> 0.433 ms at 10^6 nodes; shuttle 24:
+// 0.381 -> 0.353 ms); -DPCX_TWO_PASS=0 restores the fused single pass.
 #ifndef PCX_TWO_PASS
-#define PCX_TWO_PASS 0
+#define PCX_TWO_PASS 1
+#endif
+#ifndef PCX_TWO_PASS_MIN
+#define PCX_TWO_PASS_MIN 16
+#endif
+#ifndef PCX_STAGGER_NS
+#define PCX_STAGGER_NS 0
+#endif
+#ifndef PCX_INTERLEAVE_PHASES
+#define PCX_INTERLEAVE_PHASES 0
 #endif
 // timing experiments only (wrong results): keep the arithmetic, drop the stores
 #ifndef PCX_KO_HST
@@ -179,6 +191,72 @@ __device__ __forceinline__ double pcx_ld_f64(const double* ptr) {
 // contraction, so e.g. 1000 * (-0.4) + 500 is exactly 100 as it is in CasADi.
 __device__ __forceinline__ double pcx_unscale(double V, double xt, double r) {
     return __dadd_rn(__dmul_rn(V, xt), r);
+}
+
+// Multi-wave grids of equal tiles: every CTA of the first wave starts its data phase at
+// the same instant (when the previous kernel completes) and takes equally long, so the
+// whole GPU moves in lock-step -- all resident tiles in their store phase at once (a
+// burst the memory system cannot absorb: the queue makes them FINISH together again),
+// all computing at once (memory idle).  Spreading the first wave's start times
+// uniformly over one tile lifetime, AFTER the dependency wait, makes the store demand
+// smooth; below capacity nothing queues, lifetimes stay equal and the phases stay spread.
+__device__ __forceinline__ void pcx_first_wave_stagger() {
+#if PCX_STAGGER_NS > 0
+    unsigned nsm;
+    asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+    const unsigned first = nsm * PCX_MIN_BLOCKS;
+    if (blockIdx.x < first && blockIdx.x > 0) {
+        if (threadIdx.x == 0) {
+            // CTAs that share an SM have neighbouring indices (the block scheduler fills
+            // an SM before it moves on) or indices one SM count apart: either way
+            // i mod R differs between them, so that is the coarse part of the delay
+            const unsigned i = blockIdx.x, R = PCX_MIN_BLOCKS;
+            const unsigned long long wait_ns =
+                (unsigned long long)((i % R) * (first / R) + i / R) * PCX_STAGGER_NS / first;
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            do {
+                __nanosleep(200);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            } while (t1 - t0 < wait_ns);
+        }
+        __syncthreads();
+    }
+#endif
+}
+
+// The tiles that share an SM take turns in their Jacobian scatter (two-pass form).
+// Resident CTAs of a multi-wave grid of equal tiles run in lock-step (same start, same
+// duration: 77 % of Delta III's CTAs start within 1 us of another CTA of their SM), so
+// all of them scatter at once -- each at a third of the SM's SM->L2 store rate -- and
+// all compute at once with the store path idle.  A per-SM token serialises the
+// scatters; the waiting order it creates de-phases the tiles for the rest of the
+// launch (24 %; scatter phase 7.0 -> 4.8 us, profiles/r02_d3_lockstep.txt).  The
+// holder never waits for another CTA, so the token cannot deadlock; a stale one
+// (aborted launch) is stepped over after 200 us.
+#ifndef PCX_STORE_TOKEN
+#define PCX_STORE_TOKEN 1
+#endif
+__device__ unsigned pcx_sm_token[1024];
+// returns the token's index (thread 0), to be handed to the release
+__device__ __forceinline__ unsigned pcx_store_token_acquire(const int tid) {
+    unsigned smid = 0;
+    if (tid == 0) {
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        smid &= 1023u;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (atomicCAS(&pcx_sm_token[smid], 0u, 1u) != 0u) {
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 200000ull) break;
+        }
+    }
+    __syncthreads();
+    return smid;
+}
+__device__ __forceinline__ void pcx_store_token_release(const int tid, const unsigned smid) {
+    if (tid == 0) atomicExch(&pcx_sm_token[smid], 0u);
 }
 
 // Does this (phase, output selection) accumulate any cross-tile reduction?
@@ -580,8 +658,8 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     constexpr int NOUT = NF + Ph::ND1V + Ph::ND1S + Ph::NH2VV + Ph::NH2VS + Ph::NH2SS
                          + Ph::NHTV + Ph::NHTS;
     constexpr bool PARK = NOUT <= 40;              // small bodies: results parked in registers
-    constexpr bool TWO = (PCX_TWO_PASS != 0) && WANT_G && WANT_H && !PARK && Ph::NH2VV > 0
-                         && !Ph::STAGE_H;
+    constexpr bool TWO = (PCX_TWO_PASS != 0) && WANT_G && WANT_H && !PARK
+                         && Ph::NH2VV >= PCX_TWO_PASS_MIN && !Ph::STAGE_H;
 
     const int tid = threadIdx.x;
     PCX_STAMP(0);
@@ -642,6 +720,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     double xt_t0 = 0.0, xt_tF = 0.0;
     if (PCX_EARLY_WAIT) {
         if (!p.independent) pcx_grid_dependency_wait();
+        pcx_first_wave_stagger();
 #pragma unroll
         for (int a = 0; a < NV; ++a)
             xt0[a] = (tid < nn) ? pcx_ld_f64(x + xo + (i64)a * N + node0 + tid) : 0.0;
@@ -780,6 +859,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     // overlap freely and their load / compute / store phases interleave
     if (!PCX_EARLY_WAIT) {
         if (!p.independent) pcx_grid_dependency_wait();
+        pcx_first_wave_stagger();
         PCX_STAMP(8);
 #pragma unroll
         for (int a = 0; a < NV; ++a)
@@ -1026,6 +1106,8 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     }
 
     // ---- coalesced scatter of the Jacobian values (see pcx_store_run) ----------
+    unsigned token = 0;
+    if (TWO && PCX_STORE_TOKEN) token = pcx_store_token_acquire(tid);
     if (WANT_G) {
 #if PCX_DECODE_V1
         // (round-1 form, kept for A/B: every work item walks the table chain)
@@ -1094,6 +1176,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     // ---- second pass of the two-pass node phase ----------------------------------
     if (TWO) {
         __syncthreads();                 // the staged first derivatives have been consumed
+        if (PCX_STORE_TOKEN) pcx_store_token_release(tid, token);
         PCX_STAMP(4);
         if (active) {
             PcxNodeSink<Ph, 2> sink;     // second derivatives only; the compiler drops the rest
@@ -1384,6 +1467,41 @@ PCX_KERNEL_NAME(const __grid_constant__ PcxParams p)
     // phase trades places with the second one, so that both tiles the border
     // pass may wait for (first and last: end-node values) are dispatched first.
     tile += p.tile_begin;
+#if PCX_INTERLEAVE_PHASES
+    // Dispatch the phases round-robin instead of one after the other: every phase's
+    // copy of the generated body is then executed in every generation of CTAs and stays
+    // in L2.  Phase by phase, each phase's first generation (and the first generation
+    // of every launch) fetches ~200 KB of code per SM that a launch worth of streamed
+    // values has long evicted -- all CTAs missing on the same lines at the same time.
+    if (PCX_NUM_PHASES > 1 && p.border_mode == 0) {
+        int mmin = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < PCX_NUM_PHASES; ++q) {
+            const int n = (int)pcx_c_pbase[PCX_PHASE_PBASE(q) + PCX_PB_TILE1]
+                        - (int)pcx_c_pbase[PCX_PHASE_PBASE(q) + PCX_PB_TILE0];
+            mmin = n < mmin ? n : mmin;
+        }
+        const int i = tile;
+        if (i < mmin * PCX_NUM_PHASES) {
+            const int q = i % PCX_NUM_PHASES;
+            int t0 = 0;
+#pragma unroll
+            for (int r = 0; r < PCX_NUM_PHASES; ++r)
+                if (r == q) t0 = (int)pcx_c_pbase[PCX_PHASE_PBASE(r) + PCX_PB_TILE0];
+            tile = t0 + i / PCX_NUM_PHASES;
+        } else {
+            int j = i - mmin * PCX_NUM_PHASES;
+            bool done = false;
+#pragma unroll
+            for (int q = 0; q < PCX_NUM_PHASES; ++q) {
+                const int t0 = (int)pcx_c_pbase[PCX_PHASE_PBASE(q) + PCX_PB_TILE0];
+                const int left = (int)pcx_c_pbase[PCX_PHASE_PBASE(q) + PCX_PB_TILE1] - t0 - mmin;
+                if (!done && j < left) { tile = t0 + mmin + j; done = true; }
+                if (!done) j -= left;
+            }
+        }
+    }
+#endif
     int phase = 0;
 #pragma unroll
     for (int q = 1; q < PCX_NUM_PHASES; ++q)

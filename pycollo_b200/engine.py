@@ -293,7 +293,7 @@ def smem_bytes(S, layouts, threads):
         nout = (len(pd.fns) + len(pd.d1v) + len(pd.d1s) + len(pd.h2vv) + len(pd.h2vs)
                 + len(pd.h2ss) + len(pd.htv) + len(pd.hts))
         two_extra = 0
-        if nout > 40 and len(pd.h2vv) > 0 and not hp:
+        if nout > 40 and len(pd.h2vv) >= 16 and not hp:             # PCX_TWO_PASS_MIN
             region = (len(pd.d1v) + nds) * (NN | 1) + len(pd.d1v) * (SS + 1) + pd.NY * (NN + 24)
             two_extra = max(0, len(pd.h2vv) * threads - region)
         dbl = (len(S.btab) + SS + 1 + (pd.NY + len(pd.d1v) + nds) * (NN | 1)

@@ -10,7 +10,8 @@ from pycollo_b200 import engine as E
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 83333
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-low, _, scal = lower_case(problems.delta_iii_launch_vehicle(), "lobatto", K, 4, seed=0)
+PROBLEM = sys.argv[3] if len(sys.argv) > 3 else "delta_iii_launch_vehicle"      # any examples.problems name
+low, _, scal = lower_case(getattr(problems, PROBLEM)(), "lobatto", K, 4, seed=0)
 S = low.S
 eng = E.Engine(S, low.layouts, low.header, structure=False)
 eng.set_scaling(*scal)
@@ -27,7 +28,7 @@ eng.eval_many(what, args, 3, stream=st, gate=False, timed=False)
 torch.cuda.synchronize()
 ms = eng.eval_many(what, args, steps, stream=st, gate=True, timed=True) / steps
 alg = 8 * (S.num_x + S.nnz_g) + 8 * (S.num_x + S.num_c + S.nnz_h)
-print(json.dumps(dict(workload="delta_iii 4 phases", nodes=int(sum(t.N for t in S.ph)), tiles=int(S.num_tiles),
+print(json.dumps(dict(workload="delta_iii 4 phases" if PROBLEM.startswith("delta") else PROBLEM, nodes=int(sum(t.N for t in S.ph)), tiles=int(S.num_tiles),
                       threads=int(S.threads), ms_per_eval=round(ms, 4), algorithmic_GBs=round(alg / ms / 1e6, 1),
                       frac=round(alg / (ms * 1e-3) / 6553e9, 4),
                       env={k: v for k, v in os.environ.items() if k.startswith("PCX_")})), flush=True)

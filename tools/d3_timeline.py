@@ -57,3 +57,46 @@ stat("intra-CTA warp skew, node phase", np.nanmax(w, axis=1) - np.nanmin(w, axis
 smid = np.nan_to_num(t[:, 10]).astype(int)
 cnt = np.bincount(smid)
 print("CTAs per SM: min %d max %d" % (cnt[cnt > 0].min(), cnt.max()))
+
+# lock-step diagnostic: how many CTAs start within 1 us of another CTA's start on the same SM,
+# and how many tiles of one SM are in the scatter phase at the same time (time-weighted)
+st, en = us[:, 0], us[:, 5]
+sc0, sc1 = us[:, 2], (us[:, 4] if not np.isnan(us[:, 4]).all() else us[:, 3])
+close = tot = 0
+ov_num = ov_den = 0.0
+for sm in np.flatnonzero(cnt):
+    idx = np.flatnonzero(smid == sm)
+    a = np.sort(st[idx])
+    d = np.diff(a)
+    near = np.zeros(a.size, bool)
+    near[1:] |= d < 1.0
+    near[:-1] |= d < 1.0
+    close += int(near.sum()); tot += a.size
+    ev = sorted([(t, 1) for t in sc0[idx]] + [(t, -1) for t in sc1[idx]])
+    k = 0; last = None
+    for t, dlt in ev:
+        if last is not None and k > 0:
+            ov_num += k * k * (t - last); ov_den += k * (t - last)
+        k += dlt; last = t
+print("CTAs starting within 1 us of another on the same SM: %.0f %%" % (100.0 * close / max(tot, 1)))
+print("tiles of one SM scattering at the same time (seen by a scattering tile): %.2f" % (ov_num / max(ov_den, 1e-9)))
+# the first CTAs of a few SMs: start / scatter begin / end (us), in start order
+for sm in list(np.flatnonzero(cnt)[[0, len(np.flatnonzero(cnt)) // 2]]):
+    idx = np.flatnonzero(smid == sm)
+    idx = idx[np.argsort(st[idx])][:14]
+    print("SM %d:" % sm, " ".join("[%.1f %.1f %.1f]" % (st[i], sc0[i], en[i]) for i in idx))
+# the first generation (CTAs resident before the previous launch has completed): where does it spend its time?
+g1 = st < 20.0
+names = {0: "start", 7: "descriptor", 8: "after wait", 1: "inputs in smem", 2: "pass 1 done", 4: "scatter done",
+         15: "pass 2 done", 3: "tile done", 5: "exit"}
+print("first generation (%d CTAs), medians [p10 p90] in us:" % int(g1.sum()))
+for k in (0, 7, 8, 1, 2, 4, 15, 3, 5):
+    a = us[g1, k]; a = a[~np.isnan(a)]
+    if a.size:
+        print("  %-15s %6.1f [%6.1f %6.1f]" % (names[k], np.median(a), np.percentile(a, 10), np.percentile(a, 90)))
+g2 = (st > 50.0) & (st < 65.0)
+print("second generation (%d CTAs):" % int(g2.sum()))
+for k in (0, 7, 8, 1, 2, 4, 15, 3, 5):
+    a = us[g2, k]; a = a[~np.isnan(a)]
+    if a.size:
+        print("  %-15s %6.1f [%6.1f %6.1f]" % (names[k], np.median(a), np.percentile(a, 10), np.percentile(a, 90)))

@@ -1,0 +1,12 @@
+#!/bin/bash
+# Delta III: first-wave stagger placed after the dependency wait; shuttle with / without the two-pass form
+O=gpurun_out/r02_d3_stagger3.txt; : > $O
+for ns in 10000 19000 30000; do
+PCX_NVRTC_EXTRA="-DPCX_TWO_PASS=1 -DPCX_STAGGER_NS=$ns" python tools/d3_eval.py 83333 10 >> $O 2>&1
+done
+PCX_NVRTC_EXTRA="-DPCX_STAGGER_NS=22000" python tools/d3_eval.py 83333 10 >> $O 2>&1
+python tools/d3_eval.py 333333 10 space_shuttle_reentry >> $O 2>&1
+PCX_NVRTC_EXTRA="-DPCX_TWO_PASS=1" python tools/d3_eval.py 333333 10 space_shuttle_reentry >> $O 2>&1
+grep '^{' $O | cut -c1-300
+grep -v '^{' $O | tail -5
+PCX_NVRTC_EXTRA="-DPCX_TWO_PASS=1 -DPCX_STAGGER_NS=19000" python tools/d3_timeline.py 2>&1 | tail -16
