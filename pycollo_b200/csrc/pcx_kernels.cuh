@@ -629,10 +629,13 @@ __device__ __forceinline__ void pcx_copy_h(const double* sH, double* out_h, cons
     int dummy[] = {0, ([&] {
         constexpr int NAb = Ph::NA(Bs);
         if (NAb > 0) {
-            double* dst = out_h + pb[Ph::PB_HREG + Bs] + (m_first - 1) * NAb;
-            const double* src = sH + Ph::HB_OFF(Bs) * T;
-#pragma unroll 4
-            for (int i = tid; i < n_reg * NAb; i += T) dst[i] = src[i];
+            // trip counts are 1..NA(b): no unrolling (the unrolled form spent 20 % of the
+            // kernel's instructions on prologues / remainders of ten short loops)
+            double* dst = out_h + pb[Ph::PB_HREG + Bs] + (m_first - 1) * NAb + tid;
+            const double* src = sH + Ph::HB_OFF(Bs) * T + tid;
+            const int n = n_reg * NAb - tid;
+#pragma unroll 1
+            for (int i = 0; i < n; i += T) dst[i] = src[i];
         }
     }(), 0)...};
     (void)dummy;

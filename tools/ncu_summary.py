@@ -24,7 +24,11 @@ KEEP = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "dra
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct",
         "lts__t_bytes.sum", "derived__smsp__inst_executed_op_local_ld.sum",
         "smsp__inst_executed_op_local_st.sum", "smsp__inst_executed_op_local_ld.sum",
-        "launch__local_size_per_thread" if False else "sm__inst_executed_pipe_lsu.sum"]
+        "sm__inst_executed_pipe_lsu.sum",
+        # the SM -> L2 store path: partial-sector stores travel as full sectors
+        "l1tex__m_l1tex2xbar_write_bytes.sum", "l1tex__m_l1tex2xbar_write_bytes.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__m_l1tex2xbar_write_sectors_mem_lg_op_st.sum",
+        "lts__t_sectors_srcunit_tex_op_write.sum", "lts__t_sectors_srcunit_tex_op_write.avg.pct_of_peak_sustained_elapsed"]
 rows = list(csv.reader(open(os.path.join(G, f"raw_{tag}.csv"))))
 hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
 names, units, data = rows[hdr], rows[hdr + 1], [r for r in rows[hdr + 2:] if len(r) == len(rows[hdr])]
