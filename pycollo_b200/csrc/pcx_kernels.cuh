@@ -368,11 +368,13 @@ __device__ __forceinline__ void pcx_store_run(double* o, const int ostep, const 
 // live after it has been produced (a problem like the Delta III launcher has
 // ~90 results per node; held in arrays they alone overflow the register file).
 // ---------------------------------------------------------------------------
-template <class Ph, int MODE = 0>      // 0: every output, 1: first derivatives only, 2: second only
+// MODE 0: every output; 1: first derivatives only; 2: second derivatives only, node-diagonal
+// Hessian entries staged in output order; 3: every output, Hessian entries staged likewise
+template <class Ph, int MODE = 0>
 struct PcxNodeSink {
     static constexpr int F_ = PCX_FLAGS;
     static constexpr bool FIRST = MODE != 2, SECOND = MODE != 1;
-    static constexpr bool STG_H = Ph::STAGE_H || MODE == 2;
+    static constexpr bool STG_H = Ph::STAGE_H || MODE >= 2;
     static constexpr int HSTR = MODE == 2 ? Ph::HPS : Ph::HP;
     static constexpr bool WANT_C = (F_ & PCX_F_C) != 0, WANT_DY = (F_ & PCX_F_DY) != 0;
     static constexpr bool WANT_G = (F_ & PCX_F_G) != 0, WANT_H = (F_ & PCX_F_H) != 0;
@@ -437,7 +439,7 @@ struct PcxNodeSink {
         if (!WANT_H || !SECOND || !owned) return;
         if (PCX_KO_HST) { if (ps[Ph::OFF_H2VV + K] * val == 1.2345e-300) pcx_ko_sink = val; return; }
         if (regular) {
-            if (MODE == 2)
+            if (MODE >= 2)
                 // output order: block b of the tile's regular nodes is one contiguous
                 // run of NA(b) entries per node -- the flush is a straight copy
                 sH[Ph::HB_OFF(Ph::H2VV_B(K)) * PCX_THREADS + hrow * Ph::NA(Ph::H2VV_B(K))
@@ -665,6 +667,11 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     constexpr bool PARK = NOUT <= 40;              // small bodies: results parked in registers
     constexpr bool TWO = (PCX_TWO_PASS != 0) && WANT_G && WANT_H && !PARK
                          && Ph::NH2VV >= PCX_TWO_PASS_MIN && !Ph::STAGE_H;
+    // launches without the Jacobian (the Hessian callback of a host solver) stage nothing
+    // for a scatter: the same full-sector Hessian flush fits next to the multipliers in
+    // a single pass
+    constexpr bool HST = (PCX_TWO_PASS != 0) && !WANT_G && WANT_H && !PARK
+                         && Ph::NH2VV >= PCX_TWO_PASS_MIN && !Ph::STAGE_H;
 
     const int tid = threadIdx.x;
     PCX_STAMP(0);
@@ -755,6 +762,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
     // two-pass node phase: the second pass stages NH2VV * T Hessian entries over
     // sD / sDP / sDS / sLam, all dead once the Jacobian has been scattered
     if (TWO && sD + Ph::NH2VV * T > sRed) sRed = sD + Ph::NH2VV * T;
+    if (HST) sRed = sH + Ph::NH2VV * T;
     int* sSecNode = reinterpret_cast<int*>(sRed + T / 32);     // nsec+2 (prev first)
     int* sSecOrder = sSecNode + (nsec + 2);                    // nsec+1 (prev first)
     int* sNodeSec = sSecOrder + (nsec + 1);                    // nn
@@ -1003,6 +1011,12 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
             PcxNodeSink<Ph, 1> sink;                 // first pass: f, first derivatives
             PCX_SINK_SETUP(sink)
             Ph::eval(v, muh, mut, sink);
+        } else if (HST) {
+            PcxNodeSink<Ph, 3> sink;                 // single pass, Hessian staged for the flush
+            PCX_SINK_SETUP(sink)
+            sink.sH = sH;
+            sink.hrow = ml - ((node0 == 0) ? 1 : 0);
+            Ph::eval(v, muh, mut, sink);
         } else {
             PcxNodeSink<Ph> sink;
             PCX_SINK_SETUP(sink)
@@ -1057,6 +1071,11 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         }
     };
     if (!TWO) signal_border();
+    if (HST) {
+        const int a0 = (node0 == 0) ? 1 : 0;               // node 0 / N-1 go through irr
+        pcx_copy_h<Ph>(sH, out_h, pb, node0 + a0, (nn - 1) - a0, tid,
+                       typename PcxMakeSeq<NV>::type());
+    }
     // ---- staged Hessian entries of the tile's regular nodes, block by block ------
     if (WANT_H && Ph::STAGE_H) {
         const int a0 = (node0 == 0) ? 1 : 0;               // node 0 / N-1 go through irr

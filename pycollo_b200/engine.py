@@ -294,7 +294,9 @@ def smem_bytes(S, layouts, threads):
                 + len(pd.h2ss) + len(pd.htv) + len(pd.hts))
         two_extra = 0
         if nout > 40 and len(pd.h2vv) >= 16 and not hp:             # PCX_TWO_PASS_MIN
-            region = (len(pd.d1v) + nds) * (NN | 1) + len(pd.d1v) * (SS + 1) + pd.NY * (NN + 24)
+            # (the Hessian-only variant stages them NEXT to the multipliers: the room is
+            # what the first-derivative staging of the fused variant occupies)
+            region = (len(pd.d1v) + nds) * (NN | 1) + len(pd.d1v) * (SS + 1)
             two_extra = max(0, len(pd.h2vv) * threads - region)
         dbl = (len(S.btab) + SS + 1 + (pd.NY + len(pd.d1v) + nds) * (NN | 1)
                + len(pd.d1v) * (SS + 1)
