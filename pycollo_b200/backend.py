@@ -483,6 +483,45 @@ class Cuda:
         self.s_var_slice = slice(v, v + self.ir.n_s)
         self.c_endpoint_slice = slice(c, c + self.ir.n_b)
 
+    # -- symbol primitives of the backend (backend.py:81-124, 1343-1384) ----
+    # The CUDA backend is sympy-native: the user's symbols ARE its symbols, so the
+    # substitution that the CasADi backend performs (sympy -> SX through
+    # `user_to_backend_mapping`) reduces to resolving auxiliary data and folded
+    # constants -- exactly what the expressions handed to the code generator went through.
+    @staticmethod
+    def sym(name, rows=1, cols=1):
+        import sympy
+        if rows == 1 and cols == 1:
+            return sympy.Symbol(name)
+        return sympy.Matrix(rows, cols, lambda i, j: sympy.Symbol(f"{name}_{i}_{j}"))
+
+    @staticmethod
+    def const(val):
+        import sympy
+        return sympy.Float(val)
+
+    def substitute_pycollo_sym(self, expr, phase=None):
+        """Expression over the backend's variables: auxiliary data resolved (with the
+        phase's shadowing when ``phase`` -- an index or a phase IR -- is given) and
+        constant variables folded (``backend.py:1351-1380``)."""
+        import sympy
+        if isinstance(expr, (list, tuple)):
+            return type(expr)(self.substitute_pycollo_sym(e, phase) for e in expr)
+        if isinstance(expr, sympy.MatrixBase):
+            return expr.applyfunc(lambda e: self.substitute_pycollo_sym(e, phase))
+        if phase is None:
+            return self.ir.lower_point(expr, f"'{expr}'")
+        ph = self.p[phase] if isinstance(phase, (int, np.integer)) else phase
+        return ph.lower(expr, f"'{expr}'")
+
+    @staticmethod
+    def expr_as_numeric(expr):
+        """``backend.py:1382-1384``: a closed expression as float64."""
+        import sympy
+        if isinstance(expr, sympy.MatrixBase):
+            return np.array(expr.evalf(), dtype=np.float64)
+        return np.float64(sympy.sympify(expr).evalf())
+
     # -- construction steps (optimal_control_problem.py:316-337) ----------
     def create_bounds(self):
         self.bounds = Bounds(self.ir)
@@ -597,6 +636,55 @@ class Cuda:
         cls = NlpCallbacks if int(self.ocp.settings.derivative_level) >= 2 \
             else NlpCallbacksFirstOrder
         return cls(self._it(), ordering, x_check, register_inputs)
+
+    # -- the callables IterationScaling consumes (scaling.py:361-362, 392-394) ----
+    def g_iter_scale_callable(self, x_and_w):
+        """``[x_tilde; w_J] -> gradient`` with the objective scale taken from the
+        argument instead of the engine's current scaling (``backend.py:1506-1511``): the
+        gradient is linear in ``w_J``."""
+        xw = np.asarray(x_and_w, dtype=np.float64).ravel()
+        it = self._it()
+        x, w_arg = xw[:it.S.num_x], xw[it.S.num_x:]
+        g = self.evaluate_g(x)
+        w_now = float(getattr(getattr(it, "scaling", None), "w", 1.0))
+        return g * (float(w_arg[0]) / w_now) if w_arg.size and w_now != 0.0 else g
+
+    def G_iter_scale_callable(self, x_and_W):
+        """``[x_tilde; W] -> G`` (scipy COO, CCS entry order) with the OCP-level
+        constraint scales taken from the argument (``backend.py:1674-1679``): row i of G
+        is linear in its constraint's scale."""
+        xw = np.asarray(x_and_W, dtype=np.float64).ravel()
+        it = self._it()
+        S = it.S
+        x, W_arg = xw[:S.num_x], xw[S.num_x:]
+        vals = self.evaluate_G_nonzeros(x)
+        rows, cols = S.G_structure()
+        sc = getattr(it, "scaling", None)
+        if W_arg.size and sc is not None:
+            ratio = sc._expand_c_to_mesh(W_arg) / sc._expand_c_to_mesh(sc.W_ocp)
+            vals = vals * ratio[rows]
+        return sparse.coo_matrix((vals, (rows, cols)), shape=(S.num_c, S.num_x))
+
+    def evaluate_dy_on_mesh(self, mesh, x_user, batch=1, device=0):
+        """State derivatives ``f(x)`` at every node of ANOTHER mesh of the same problem,
+        in the user basis -- the hook that replaces the SX-coupled attributes
+        ``mesh_refinement.py:109, 148-151`` reads (``p[i].y_eqn``, ``V/r_sym_val_mapping``)."""
+        low = lower_problem(self.ocp, mesh.p)
+        eng = _engine.Engine(low.S, low.layouts, low.header, batch=batch, device=device)
+        # user basis: V = 1, r = 0, W = 1, w = 1 (mesh_refinement.py:149-150)
+        eng.set_scaling(np.ones(low.S.n_var_ocp), np.zeros(low.S.n_var_ocp),
+                        np.ones(low.S.n_con_ocp), 1.0)
+        dy = eng.eval_host(_engine.EVAL_DY, x_user)["dy"]
+        return dy[0] if batch == 1 else dy
+
+    def process_solution(self, iteration, nlp_result):
+        """``backend.py:1830-1841``: the processed solution of an NLP result
+        (``NlpResult.solution["x"]``, optionally ``["f"]``)."""
+        from .solution import Solution
+        sol = nlp_result.solution if hasattr(nlp_result, "solution") else nlp_result
+        x = np.asarray(sol["x"], dtype=np.float64).ravel()
+        J = float(np.asarray(sol["f"]).ravel()[0]) if "f" in sol else None
+        return Solution(iteration, x, J)
 
     def solve_nlp(self):
         raise NotImplementedError(

@@ -49,6 +49,7 @@ class PhaseIR:
     y_needed: np.ndarray = None
     u_needed: np.ndarray = None
     q_needed: np.ndarray = None
+    lower: object = None      # expr -> expr over (y, u, s): aux data and constants resolved
 
     n_y = property(lambda self: len(self.y))
     n_u = property(lambda self: len(self.u))
@@ -68,6 +69,7 @@ class ProblemIR:
     s_needed: np.ndarray = None
     point_symbols: tuple = field(default_factory=tuple)
     full_bounds: dict = field(default_factory=dict)   # before constant removal
+    lower_point: object = None   # expr -> expr over the endpoint / q / t / s symbols
 
     n_s = property(lambda self: len(self.s))
     n_b = property(lambda self: len(self.b))
@@ -301,7 +303,7 @@ def build_ir(ocp) -> ProblemIR:
             t_bnd=t_bnd[t_need], y_t0_bnd=y_t0_bnd[y_need],
             y_tF_bnd=y_tF_bnd[y_need], p_bnd=p_bnd,
             t_needed=(bool(t_need[0]), bool(t_need[1])),
-            y_needed=y_need, u_needed=u_need, q_needed=q_need))
+            y_needed=y_need, u_needed=u_need, q_needed=q_need, lower=lower))
 
     # problem-level expressions see every phase's endpoint symbols
     res = _Resolver(problem_aux, point_roots)
@@ -335,4 +337,4 @@ def build_ir(ocp) -> ProblemIR:
     return ProblemIR(phases=phases, s=s_kept, J=J, b=tuple(b_exprs),
                      s_bnd=s_bnd_full[s_needed], b_bnd=b_bnd, s_needed=s_needed,
                      point_symbols=tuple(ordered_points),
-                     full_bounds=full_bounds)
+                     full_bounds=full_bounds, lower_point=lower_point)

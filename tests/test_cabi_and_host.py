@@ -143,3 +143,29 @@ def test_nlp_callback_orderings_are_permutations():
     assert sorted(cb.g_perm) == list(range(it.S.nnz_g))
     assert sorted(cb.h_perm) == list(range(it.S.nnz_h))
     assert pycollo_b200.__version__
+
+
+def test_backend_symbol_primitives():
+    """``sym / const / substitute_pycollo_sym / expr_as_numeric`` of the backend surface
+    (``pycollo/backend.py:81-124, 1343-1384``): the CUDA backend is sympy-native, so the
+    substitution resolves auxiliary data (phase-level shadowing included) and folds
+    constant variables -- the expressions the code generator sees."""
+    import sympy as sym
+    from examples import problems
+    from pycollo_b200.backend import Cuda
+    ocp = problems.double_pendulum()
+    ocp.settings.defer_engine = True
+    b = Cuda(ocp)
+    assert b.sym("a") == sym.Symbol("a") and b.sym("M", 2, 3).shape == (2, 3)
+    assert b.const(2.5) == sym.Float(2.5)
+    assert b.expr_as_numeric(sym.Float(1.5) * 2) == 3.0 and b.expr_as_numeric(sym.Integer(2)).dtype == np.float64
+    ph = ocp.phases[0]
+    lowered = [b.substitute_pycollo_sym(e, 0) for e in ph.state_equations]
+    roots = set(b.p[0].y) | set(b.p[0].u) | set(b.ir.s)
+    assert all(e.free_symbols <= roots for e in lowered)            # aux data resolved
+    assert tuple(lowered) == tuple(b.p[0].f)                        # = what codegen was given
+    assert b.substitute_pycollo_sym(tuple(ph.state_equations), b.p[0]) == tuple(lowered)
+    J = b.substitute_pycollo_sym(ocp.objective_function)
+    assert J == b.ir.J and J.free_symbols <= set(b.ir.point_symbols)
+    with pytest.raises(ValueError, match="not defined"):
+        b.substitute_pycollo_sym(sym.Symbol("nobody_defined_me") + 1, 0)

@@ -212,6 +212,37 @@ def test_cyipopt_adapter_orderings_and_staging():
         ocp1._backend.evaluate_H_nonzeros(x1, 1.0, None)
 
 
+def test_backend_surface_callables():
+    """The callables the rest of pycollo reaches for on a backend:
+    ``g_iter_scale_callable([x; w])``, ``G_iter_scale_callable([x; W])``
+    (``scaling.py:361-362, 392-394``), ``evaluate_dy_on_mesh`` (the hook replacing what
+    ``mesh_refinement.py:109, 148-151`` reads) and ``process_solution``."""
+    from pycollo_b200.backend import NlpResult
+    ocp = examples.free_flying_robot()
+    examples.set_mesh(ocp, 9, 4)
+    ocp.initialise()
+    b = ocp._backend
+    it = b.current_iteration
+    rng = np.random.default_rng(4)
+    x = it.guess_x_tilde + 0.01 * rng.standard_normal(it.num_x)
+    sc = it.scaling
+    # the scales of the argument replace the engine's: linear in w / row-wise linear in W
+    g = b.evaluate_g(x)
+    assert max_err(b.g_iter_scale_callable(np.append(x, 3.0 * sc.w)), 3.0 * g) <= 1e-15
+    G = b.evaluate_G(x).tocsr()
+    W2 = sc.W_ocp * rng.uniform(0.5, 2.0, sc.W_ocp.size)
+    G2 = b.G_iter_scale_callable(np.concatenate([x, W2])).tocsr()
+    ratio = sc._expand_c_to_mesh(W2) / sc.W
+    assert abs(G2 - G.multiply(ratio[:, None]).tocsr()).max() <= 1e-12 * abs(G).max()
+    assert np.array_equal(b.G_iter_scale_callable(x).toarray(), G.toarray())
+    # dy on a mesh given from outside, user basis: the iteration's own mesh reproduces dy
+    dy = b.evaluate_dy_on_mesh(it.mesh, sc.unscale_x(x))
+    assert max_err(dy, b.evaluate_dy(x)) <= 1e-12
+    sol = b.process_solution(it, NlpResult(solution={"x": x, "f": b.evaluate_J(x)}, info=None,
+                                           solve_time=0.0))
+    assert sol.J == b.evaluate_J(x) and np.array_equal(sol.x, x)
+
+
 def test_cyipopt_adapter_uploads_from_the_callers_arrays():
     """``register_inputs``: the caller's x / multiplier arrays are page-locked on first
     sight and become the DMA source (no staging copy).  Results equal the staging
