@@ -18,6 +18,7 @@ trigger a recompile.
 from __future__ import annotations
 
 import hashlib
+import re
 
 import sympy as sym
 from sympy.printing.c import C99CodePrinter
@@ -186,9 +187,12 @@ def _emit_program(inputs, outputs, indent="        "):
 class PhaseLayout:
     """Offsets of the per-phase runtime tables (pscal: doubles, pbase: int64)."""
 
-    def __init__(self, pd, has_t0, has_tF, pscal_off, pbase_off):
+    def __init__(self, pd, has_t0, has_tF, pscal_off, pbase_off, kc=()):
         NV, NF, NY = pd.NV, pd.NF, pd.NY
         self.pd = pd
+        # literals of a SHARED expression body that differ between the phases sharing it
+        # (see share_groups): this phase's values, last block of its pscal table
+        self.kc = [float(z) for z in kc]
         self.has_t0, self.has_tF = has_t0, has_tF
         o = 0
         self.ps = {}
@@ -196,7 +200,7 @@ class PhaseLayout:
                         ("D1S", len(pd.d1s)), ("GCST", 1 + 2 * NY),
                         ("H2VV", len(pd.h2vv)), ("H2VS", len(pd.h2vs)),
                         ("HT0", len(pd.htv)), ("HTF", len(pd.htv)),
-                        ("GT0", NY), ("GTF", NY), ("TINFO", 4)):
+                        ("GT0", NY), ("GTF", NY), ("TINFO", 4), ("KC", len(self.kc))):
             self.ps[name] = o
             o += n
         self.pscal_size = o
@@ -233,11 +237,56 @@ def stage_h_rule(n_h2vv):
     return bool(int(os.environ.get("PCX_STAGE_H", "0"))) and n_h2vv > 0
 
 
-def generate(ir, phase_derivs, point_derivs, structure):
+_LITERAL = re.compile(r"(?<![\w.])(?:\d+\.\d*(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+)(?![\w.])")
+
+
+def share_bodies_default():
+    """Phases whose generated structs are textually identical up to the values of their
+    floating-point literals share ONE instantiation of the tile function (Delta III: four
+    phases, one 185 KB body instead of four; the literals that differ -- thrust, mass flow --
+    are read from the phase's constant table).  ``PCX_SHARE_BODIES=0`` switches it off."""
+    import os
+    return bool(int(os.environ.get("PCX_SHARE_BODIES", "1")))
+
+
+def share_groups(signatures, bodies):
+    """``leader[q]`` = first phase with phase q's signature (dimension tables + body text
+    with every float literal blanked); per phase the values of the literals that differ
+    inside its group, in slot order; per leader the body text reading those from ``kc``."""
+    P = len(bodies)
+    leader = list(range(P))
+    first = {}
+    for q in range(P):
+        leader[q] = first.setdefault(signatures[q], q)
+    kc = [[] for _ in range(P)]
+    shared_body = {}
+    for r in sorted(set(leader)):
+        group = [q for q in range(P) if leader[q] == r]
+        if len(group) < 2:
+            continue
+        lits = [_LITERAL.findall(bodies[q]) for q in group]
+        slots, slot_of = {}, {}
+        for i in range(len(lits[0])):
+            key = tuple(l[i] for l in lits)
+            if len(set(key)) > 1:
+                slot_of[i] = slots.setdefault(key, len(slots))
+        for g, q in enumerate(group):
+            kc[q] = [float(key[g]) for key in slots]          # dicts keep insertion order
+        counter = iter(range(len(lits[0])))
+
+        def put(m):
+            i = next(counter)
+            return f"kc[{slot_of[i]}]" if i in slot_of else m.group(0)
+        shared_body[r] = _LITERAL.sub(put, bodies[r])
+    return leader, kc, shared_body
+
+
+def generate(ir, phase_derivs, point_derivs, structure, share=None):
     """Return (header_source, layouts)."""
     P = len(ir.phases)
     NS, NB = ir.n_s, ir.n_b
     npt = len(point_derivs.pts)
+    share = share_bodies_default() if share is None else bool(share)
     out = ["// generated by pycollo_b200.codegen -- do not edit\n",
            "#pragma once\n",
            f"#define PCX_NUM_PHASES {P}\n#define PCX_NS {NS}\n#define PCX_NB {NB}\n",
@@ -251,14 +300,25 @@ def generate(ir, phase_derivs, point_derivs, structure):
            f"#define PCX_BV_IRR {structure.bv_irr0}\n",
            "#define PCX_FOREACH_PHASE(X) " + " ".join(f"X({q})" for q in range(P)) + "\n",
            "template <int P> struct PcxPhase;\n"]
+    # the expression bodies (the expensive part: one sympy.cse program per phase), then
+    # the phases that may share one
+    bodies = [_phase_body(pd, NS) for pd in phase_derivs]
+    leader, kcs, shared_body = list(range(P)), [[] for _ in range(P)], {}
+    if share and P > 1:
+        sig = [(_phase_dims(pd, PhaseLayout(pd, ph.t_needed[0], ph.t_needed[1], 0, 0)),
+                _LITERAL.sub("#", bodies[q]))
+               for q, (ph, pd) in enumerate(zip(ir.phases, phase_derivs))]
+        leader, kcs, shared_body = share_groups(sig, bodies)
     layouts = []
     ps_off = pb_off = 0
     for q, (ph, pd) in enumerate(zip(ir.phases, phase_derivs)):
-        lay = PhaseLayout(pd, ph.t_needed[0], ph.t_needed[1], ps_off, pb_off)
+        lay = PhaseLayout(pd, ph.t_needed[0], ph.t_needed[1], ps_off, pb_off, kcs[q])
+        lay.leader = leader[q]
         layouts.append(lay)
         ps_off += lay.pscal_size
         pb_off += lay.pbase_size
-        out.append(_phase_struct(q, ph, pd, lay, NS))
+        out.append(_phase_struct(q, pd, lay, leader[q], q in shared_body,
+                                 shared_body.get(q, bodies[q])))
     out.insert(2, f"#define PCX_PSCAL_TOTAL {ps_off}\n#define PCX_PBASE_TOTAL {pb_off}\n"
                   f"#define PCX_GSCAL_TOTAL {2 * NS + 1 + NB}\n")
     out.append(_gfun("PCX_PHASE_NRED", [l.nred for l in layouts]))
@@ -266,6 +326,7 @@ def generate(ir, phase_derivs, point_derivs, structure):
     out.append(_gfun("PCX_PHASE_PBASE", [l.pbase_off for l in layouts]))
     out.append(_gfun("PCX_PHASE_PSCAL", [l.pscal_off for l in layouts]))
     out.append(_gfun("PCX_PHASE_TINFO", [l.ps["TINFO"] for l in layouts]))
+    out.append(_gfun("PCX_PHASE_LEADER", leader))
     pb0 = layouts[0].pb
     out.append(f"#define PCX_PB_T0X {pb0['T0X']}\n#define PCX_PB_TFX {pb0['TFX']}\n"
                f"#define PCX_PB_TILE0 {pb0['TILE0']}\n#define PCX_PB_TILE1 {pb0['TILE1']}\n")
@@ -274,7 +335,10 @@ def generate(ir, phase_derivs, point_derivs, structure):
     return src, layouts
 
 
-def _phase_struct(q, ph, pd, lay, NS):
+def _phase_dims(pd, lay):
+    """The constexpr members of ``PcxPhase<q>`` that do not depend on where the phase
+    sits in the problem (dimensions, table offsets inside the phase's own blocks,
+    pattern lookups): phases may share a body only if these agree."""
     NV, NF, NY = pd.NV, pd.NF, pd.NY
     fam_code = {"d": 0, "p": 1, "i": 2}
     pairs_by_b = {}
@@ -287,9 +351,7 @@ def _phase_struct(q, ph, pd, lay, NS):
         nA[b] = len(lst)
         for i, (_, k) in enumerate(lst):
             pos[k] = i
-    s = [f"template <> struct PcxPhase<{q}> {{\n",
-         f"    static constexpr int INDEX = {q};\n",
-         f"    static constexpr int NY = {NY}, NU = {pd.NU}, NV = {NV}, NP = {pd.NP}, "
+    s = [f"    static constexpr int NY = {NY}, NU = {pd.NU}, NV = {NV}, NP = {pd.NP}, "
          f"NQ = {pd.NQ}, NF = {NF};\n",
          f"    static constexpr int ND1V = {len(pd.d1v)}, ND1S = {len(pd.d1s)}, "
          f"ND1SD = {sum(1 for e, _ in pd.d1s if pd.fam[e] == 'd')};\n",
@@ -298,8 +360,7 @@ def _phase_struct(q, ph, pd, lay, NS):
          f"    static constexpr bool HAS_T0 = {'true' if lay.has_t0 else 'false'}, "
          f"HAS_TF = {'true' if lay.has_tF else 'false'};\n",
          f"    static constexpr int NRED = {lay.nred}, RED_G = {lay.red_g}, "
-         f"RED_GS = {lay.red_gs}, RED_HTS = {lay.red_hts}, RED_HSS = {lay.red_hss};\n",
-         f"    static constexpr int PSCAL_OFF = {lay.pscal_off}, PBASE_OFF = {lay.pbase_off};\n"]
+         f"RED_GS = {lay.red_gs}, RED_HTS = {lay.red_hts}, RED_HSS = {lay.red_hss};\n"]
     for name, o in lay.ps.items():
         s.append(f"    static constexpr int OFF_{name} = {o};\n")
     for name, o in lay.pb.items():
@@ -321,8 +382,38 @@ def _phase_struct(q, ph, pd, lay, NS):
     # stride of a node's row of staged node-diagonal entries in the two-pass node phase
     s.append(f"    static constexpr int HPS = {len(pd.h2vv) | 1};\n")
     s.append(_cfun("HB_OFF", hb_off))
+    return "".join(s)
 
-    # ---- the expression body ----
+
+def _phase_struct(q, pd, lay, leader, shared, body):
+    """``PcxPhase<q>``.  ``shared``: this instantiation also serves other phases -- the
+    skeleton then takes the table offsets of the phase at hand at run time instead of
+    ``PSCAL_OFF`` / ``PBASE_OFF`` / ``INDEX``.  A phase with a ``leader`` other than
+    itself forwards ``eval`` to the leader's body (the skeleton never instantiates it:
+    it dispatches ``pcx_tile<PcxPhase<PCX_PHASE_LEADER(q)>>``)."""
+    s = [f"template <> struct PcxPhase<{q}> {{\n",
+         f"    static constexpr int INDEX = {q}, LEADER = {leader}, NKC = {len(lay.kc)};\n",
+         f"    static constexpr bool SHARED = {'true' if shared else 'false'};\n",
+         f"    static constexpr int PSCAL_OFF = {lay.pscal_off}, PBASE_OFF = {lay.pbase_off};\n",
+         _phase_dims(pd, lay)]
+    # results are handed to a sink (``o.template D1V<k>(value)`` ...) the moment
+    # they exist instead of being returned in arrays: with tens of outputs per
+    # node the arrays alone would not fit the register file
+    s.append("    template <class Sink>\n"
+             "    static __device__ __forceinline__ void eval(\n"
+             "        const double* __restrict__ v, const double* __restrict__ muh,\n"
+             "        const double* __restrict__ mut, const double* __restrict__ kc, Sink& o) {\n")
+    if leader != q:
+        s.append(f"        PcxPhase<{leader}>::eval(v, muh, mut, kc, o);")
+    else:
+        s.append(body)
+    s.append("\n    }\n};\n")
+    return "".join(s)
+
+
+def _phase_body(pd, NS):
+    """The straight-line program of one phase's node functions."""
+    NV, NF = pd.NV, pd.NF
     vsyms = [sym.Symbol(f"v{a}") for a in range(NV + NS)]
     sub = dict(zip(pd.variables, vsyms))
     muh = [sym.Symbol(f"mh{e}") for e in range(NF)]
@@ -357,16 +448,7 @@ def _phase_struct(q, ph, pd, lay, NS):
     inputs = [(f"v{a}", f"v[{a}]") for a in range(NV + NS)]
     inputs += [(f"mh{e}", f"muh[{e}]") for e in range(NF)]
     inputs += [(f"mt{e}", f"mut[{e}]") for e in range(NF)]
-    # results are handed to a sink (``o.template D1V<k>(value)`` ...) the moment
-    # they exist instead of being returned in arrays: with tens of outputs per
-    # node the arrays alone would not fit the register file
-    s.append("    template <class Sink>\n"
-             "    static __device__ __forceinline__ void eval(\n"
-             "        const double* __restrict__ v, const double* __restrict__ muh,\n"
-             "        const double* __restrict__ mut, Sink& o) {\n")
-    s.append(_emit_program(inputs, outputs))
-    s.append("\n    }\n};\n")
-    return "".join(s)
+    return _emit_program(inputs, outputs)
 
 
 def _point_function(ptd, NB):

@@ -646,7 +646,7 @@ __device__ __forceinline__ void pcx_copy_h(const double* sH, double* out_h, cons
 }
 
 template <class Ph>
-__device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
+__device__ void pcx_tile(const PcxParams& p, const int tile, const int inst, const int phase,
                          unsigned char* smem_raw, PcxTileStatic& ts)
 {
     constexpr int F = PCX_FLAGS;
@@ -675,12 +675,16 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
 
     const int tid = threadIdx.x;
     PCX_STAMP(0);
-    const i64* pb = pcx_c_pbase + Ph::PBASE_OFF;
-    const double* ps = pcx_c_pscal + Ph::PSCAL_OFF;
+    // An instantiation that serves several phases (identical bodies up to a few literals,
+    // codegen.py: share_groups) finds the tables of the phase at hand at run time; one that
+    // serves a single phase keeps compile-time constant-bank addresses.
+    const i64* pb = pcx_c_pbase + (Ph::SHARED ? PCX_PHASE_PBASE(phase) : Ph::PBASE_OFF);
+    const double* ps = pcx_c_pscal + (Ph::SHARED ? PCX_PHASE_PSCAL(phase) : Ph::PSCAL_OFF);
+    const double* kc = ps + Ph::OFF_KC;
     const i64 N = pb[Ph::PB_N], K = pb[Ph::PB_K];
     const i64 xo = pb[Ph::PB_XOFF], co = pb[Ph::PB_COFF];
     const i64 sec_off = pb[Ph::PB_SECOFF];         // offset into sec_order/h/type
-    const i64* sec_node = p.sec_node + sec_off + Ph::INDEX;   // K+1 per phase
+    const i64* sec_node = p.sec_node + sec_off + (Ph::SHARED ? phase : Ph::INDEX);   // K+1 per phase
     const unsigned long long keep = pcx_policy_keep();
     const double* x = p.x + (i64)inst * p.num_x;
     const double* lam = WANT_H ? p.lam + (i64)inst * p.num_c : nullptr;
@@ -996,7 +1000,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         // exists: staged (G), stored (H, dy, path rows of c) or accumulated
         if (PARK) {
             PcxParkingSink<Ph> parked;
-            Ph::eval(v, muh, mut, parked);
+            Ph::eval(v, muh, mut, kc, parked);
             PcxNodeSink<Ph> sink;
             PCX_SINK_SETUP(sink)
             pcx_drain_F(parked, sink, typename PcxMakeSeq<NF>::type());
@@ -1010,17 +1014,17 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
         } else if (TWO) {
             PcxNodeSink<Ph, 1> sink;                 // first pass: f, first derivatives
             PCX_SINK_SETUP(sink)
-            Ph::eval(v, muh, mut, sink);
+            Ph::eval(v, muh, mut, kc, sink);
         } else if (HST) {
             PcxNodeSink<Ph, 3> sink;                 // single pass, Hessian staged for the flush
             PCX_SINK_SETUP(sink)
             sink.sH = sH;
             sink.hrow = ml - ((node0 == 0) ? 1 : 0);
-            Ph::eval(v, muh, mut, sink);
+            Ph::eval(v, muh, mut, kc, sink);
         } else {
             PcxNodeSink<Ph> sink;
             PCX_SINK_SETUP(sink)
-            Ph::eval(v, muh, mut, sink);
+            Ph::eval(v, muh, mut, kc, sink);
         }
         if (WANT_GRAD && owned) {
 #pragma unroll
@@ -1207,7 +1211,7 @@ __device__ void pcx_tile(const PcxParams& p, const int tile, const int inst,
             PCX_SINK_SETUP(sink)
             sink.sH = sD;
             sink.hrow = ml - ((node0 == 0) ? 1 : 0);
-            Ph::eval(v, muh, mut, sink);
+            Ph::eval(v, muh, mut, kc, sink);
         }
         __syncthreads();
         PCX_STAMP(15);
@@ -1464,6 +1468,19 @@ __device__ __noinline__ void pcx_border(const PcxParams& p, const int inst, doub
     if (tid == 0) p.ticket[inst] = 0u;
 }
 
+// pcx_tile is instantiated for the leaders of the body-sharing groups only
+template <int P, bool IS_LEADER = (PCX_PHASE_LEADER(P) == P)> struct PcxTileOf {
+    static __device__ __forceinline__ void run(const PcxParams& p, const int tile, const int inst,
+                                               const int phase, unsigned char* smem,
+                                               PcxTileStatic& ts) {
+        pcx_tile<PcxPhase<P> >(p, tile, inst, phase, smem, ts);
+    }
+};
+template <int P> struct PcxTileOf<P, false> {
+    static __device__ __forceinline__ void run(const PcxParams&, int, int, int, unsigned char*,
+                                               PcxTileStatic&) {}
+};
+
 extern "C" __global__ void __launch_bounds__(PCX_THREADS, PCX_MIN_BLOCKS)
 PCX_KERNEL_NAME(const __grid_constant__ PcxParams p)
 {
@@ -1490,6 +1507,7 @@ PCX_KERNEL_NAME(const __grid_constant__ PcxParams p)
     // memory tile ranges, without a dependent global load.  The last tile of a
     // phase trades places with the second one, so that both tiles the border
     // pass may wait for (first and last: end-node values) are dispatched first.
+    if (p.reverse) tile = p.tile_count - 1 - tile;
     tile += p.tile_begin;
 #if PCX_INTERLEAVE_PHASES
     // Dispatch the phases round-robin instead of one after the other: every phase's
@@ -1566,8 +1584,10 @@ PCX_KERNEL_NAME(const __grid_constant__ PcxParams p)
         for (int q = 1; q < PCX_NUM_PHASES; ++q)
             if (tile >= (int)pcx_c_pbase[PCX_PHASE_PBASE(q) + PCX_PB_TILE0]) phase = q;
     }
-    switch (phase) {
-#define PCX_CASE(P) case P: pcx_tile<PcxPhase<P> >(p, tile, inst, pcx_smem, pcx_tile_static); break;
+    // one instantiation per LEADER: the phases that share a body run the leader's tile
+    // function with their own (run-time) phase index
+    switch (PCX_PHASE_LEADER(phase)) {
+#define PCX_CASE(P) case P: PcxTileOf<P>::run(p, tile, inst, phase, pcx_smem, pcx_tile_static); break;
         PCX_FOREACH_PHASE(PCX_CASE)
 #undef PCX_CASE
         default: break;

@@ -68,6 +68,11 @@ struct PcxParams {
     // iterates with distinct buffers): the kernel does not wait for that grid to
     // complete before touching its own data (scratch sets rotate on the host side)
     int rank, world, border_rank, independent;
+    // reverse != 0: this launch walks the tile list backwards.  Consecutive launches of a
+    // multi-wave grid alternate, so that a launch STARTS with the phase whose generated
+    // body the previous launch has just been executing (warm instruction caches) instead
+    // of the one it left hundreds of microseconds and a gigabyte of streamed values ago.
+    int reverse;
     u32* status;            // sticky device-side error word (0 = ok; 1 = exchange timeout)
     // tiles
     const i64* tile_desc;   // 8 per tile: phase,k0,k1,node0,nn,run0,run1,-

@@ -270,6 +270,8 @@ def scaling_tables(S, layouts, V_ocp, r_ocp, W_ocp, w):
             ps[o["GT0"] + i] = -0.5 * Vt[0] * Wf[i]
             ps[o["GTF"] + i] = 0.5 * Vt[1] * Wf[i]
         ps[o["TINFO"]:o["TINFO"] + 4] = [Vt[0], rt[0], Vt[1], rt[1]]
+        # literals of a shared expression body that differ between its phases (codegen.share_groups)
+        ps[o["KC"]:o["KC"] + len(lay.kc)] = lay.kc
         ps_all.append(ps)
     pscal = np.concatenate(ps_all)
     gscal = np.concatenate([Vs, rs, [float(w)],

@@ -38,15 +38,16 @@ struct Rec {
     template <int K> void HTS(double v) { hts[K] = v; }
 };
 template <class Ph> void run(FILE* in, int npts) {
-    const int nin = Ph::NV + PCX_NS + 2 * Ph::NF;
-    std::vector<double> buf(nin);
+    const int nin = Ph::NV + PCX_NS + 2 * Ph::NF + Ph::NKC;
+    std::vector<double> buf(nin + 1);
     for (int k = 0; k < npts; ++k) {
         for (int i = 0; i < nin; ++i) if (fscanf(in, "%lf", &buf[i]) != 1) return;
         Rec r;
         r.f.assign(Ph::NF + 1, 0); r.d1v.assign(Ph::ND1V + 1, 0); r.d1s.assign(Ph::ND1S + 1, 0);
         r.h2vv.assign(Ph::NH2VV + 1, 0); r.h2vs.assign(Ph::NH2VS + 1, 0); r.h2ss.assign(Ph::NH2SS + 1, 0);
         r.htv.assign(Ph::NHTV + 1, 0); r.hts.assign(Ph::NHTS + 1, 0);
-        Ph::eval(buf.data(), buf.data() + Ph::NV + PCX_NS, buf.data() + Ph::NV + PCX_NS + Ph::NF, r);
+        Ph::eval(buf.data(), buf.data() + Ph::NV + PCX_NS, buf.data() + Ph::NV + PCX_NS + Ph::NF,
+                 buf.data() + Ph::NV + PCX_NS + 2 * Ph::NF, r);
         auto dump = [](const std::vector<double>& a, int n) { for (int i = 0; i < n; ++i) printf("%.17g ", a[i]); };
         dump(r.f, Ph::NF); dump(r.d1v, Ph::ND1V); dump(r.d1s, Ph::ND1S); dump(r.h2vv, Ph::NH2VV);
         dump(r.h2vs, Ph::NH2VS); dump(r.h2ss, Ph::NH2SS); dump(r.htv, Ph::NHTV); dump(r.hts, Ph::NHTS);
@@ -102,7 +103,12 @@ def test_generated_bodies_match_sympy_on_the_host(name, tmp_path):
         assert "pow(" not in low.header                      # half-integer powers -> shared sqrt
     rng = np.random.default_rng(3)
     NS = low.S.NS
-    for ip in sorted({0, len(low.pds) - 1}):
+    if name == "delta_iii_launch_vehicle":
+        # the four phases differ in a handful of literals only: one shared body
+        assert [lay.leader for lay in low.layouts] == [0, 0, 0, 0]
+        assert 1 <= len(low.layouts[0].kc) <= 12
+        assert low.header.count("        const double w_0 = ") == 1   # (the point function has its own)
+    for ip in sorted({0, 1, len(low.pds) - 1} & set(range(len(low.pds)))):
         pd = low.pds[ip]
         npts = 3
         rows = []
@@ -113,13 +119,16 @@ def test_generated_bodies_match_sympy_on_the_host(name, tmp_path):
                 v[:3] *= 6.4e6                               # position outside the Earth
                 v[3:6] *= 3e3
                 v[6] *= 1e5
-            rows.append(np.concatenate([v, rng.standard_normal(pd.NF), rng.standard_normal(pd.NF)]))
+            # + the phase's own values of the literals a shared body reads from its table
+            rows.append(np.concatenate([v, rng.standard_normal(pd.NF), rng.standard_normal(pd.NF),
+                                        low.layouts[ip].kc]))
         inp = tmp_path / f"in_{ip}.txt"
         inp.write_text(f"{ip} {npts}\n" + "\n".join(" ".join(f"{z:.17g}" for z in r) for r in rows))
         out = subprocess.run([str(exe), str(inp)], capture_output=True, text=True, check=True).stdout
         got = np.array([[float(z) for z in line.split()] for line in out.strip().split("\n")])
         for r, g in zip(rows, got):
-            v, muh, mut = r[:pd.NV + NS], r[pd.NV + NS:pd.NV + NS + pd.NF], r[pd.NV + NS + pd.NF:]
+            v, muh, mut = (r[:pd.NV + NS], r[pd.NV + NS:pd.NV + NS + pd.NF],
+                           r[pd.NV + NS + pd.NF:pd.NV + NS + 2 * pd.NF])
             ref = _reference(pd, NS, v, muh, mut)
             assert g.shape == ref.shape
             scale = np.maximum(np.abs(ref), 1e-3 * np.abs(ref).max() + 1e-300)
