@@ -104,6 +104,21 @@ void pcx_destroy(pcx_engine* e);
 const char* pcx_last_error(const pcx_engine* e);
 const char* pcx_version(void);
 
+/* Creation WITHOUT Python in the process (a compiled host: IPOPT's C++ TNLP).  The
+ * problem definition is symbolic Python in the reference (OptimalControlProblem,
+ * pycollo/optimal_control_problem.py) and stays there: `Engine.save_spec(path)`
+ * (pycollo_b200/engine.py) writes, once per problem and mesh, everything pcx_create
+ * and pcx_set_scaling are given -- the generated expression bodies, the integer
+ * tables, the patterns, the scaling tables -- into one file ("PCXSPEC1": 8-byte
+ * magic; int32[10] threads, batch, num_tiles, nvmax, n_border, bv_size, nred_max,
+ * btab_len, reserved, num_tables; int64[6] num_x, num_c, num_dy, nnz_g, nnz_h,
+ * smem_bytes; int64 header length + text; per table int64 name length + name +
+ * int64 bytes + data; int64[4] lengths of pscal / gscal / border_coef / pt_scal +
+ * doubles; every block padded to 8 bytes; little endian).  This call reads it,
+ * creates the engine on `device` and sets the stored scaling (if any).
+ * PCX_EINVAL: unreadable file, bad magic, truncated or inconsistent contents.   */
+int  pcx_create_from_file(const char* path, int device, pcx_engine** out);
+
 /* names / element sizes of the tables pcx_create expects */
 int         pcx_table_count(void);
 const char* pcx_table_name(int i);

@@ -74,6 +74,7 @@ def load_library(rebuild=False):
     lib.pcx_table_name.argtypes = [i32]
     lib.pcx_table_elem_size.argtypes = [i32]
     lib.pcx_create.argtypes = [ctypes.POINTER(_Spec), ctypes.POINTER(vp)]
+    lib.pcx_create_from_file.argtypes = [ctypes.c_char_p, i32, ctypes.POINTER(vp)]
     lib.pcx_destroy.argtypes = [vp]
     lib.pcx_destroy.restype = None
     lib.pcx_set_scaling.argtypes = [vp, dp, i64, dp, i64, dp, i64, dp, i64]
@@ -328,6 +329,28 @@ class Engine:
 
     def __init__(self, S, layouts, header, *, batch=1, device=0, min_blocks=None,
                  structure=None):
+        spec = self._prepare(S, layouts, header, batch, device, min_blocks, structure)
+        h = ctypes.c_void_p()
+        rc = self.lib.pcx_create(ctypes.byref(spec), ctypes.byref(h))
+        if rc != 0:
+            raise PcxError(f"pcx_create failed ({rc}): "
+                           f"{self.lib.pcx_last_error(None).decode(errors='replace')}")
+        self.h = h
+
+    @classmethod
+    def write_spec(cls, path, S, layouts, header, scaling=None, *, batch=1, min_blocks=None,
+                   structure=None):
+        """``save_spec`` without creating an engine (no device needed): the file a
+        compiled host hands to ``pcx_create_from_file``.  ``scaling`` =
+        ``(V_ocp, r_ocp, W_ocp, w)`` or None."""
+        self = cls.__new__(cls)
+        self.h = None
+        self._prepare(S, layouts, header, batch, 0, min_blocks, structure)
+        if scaling is not None:
+            self._scal = scaling_tables(S, layouts, *scaling)
+        return self.save_spec(path)
+
+    def _prepare(self, S, layouts, header, batch, device, min_blocks, structure):
         self.lib = load_library()
         self.S, self.layouts = S, layouts
         self.batch = int(batch)
@@ -353,34 +376,31 @@ class Engine:
             if len(cr):
                 extra.append((b"g_const_ranges", cr.ravel()))
         arr = (_Table * (n + len(extra)))()
-        self._keep = []
+        self._keep, self._table_names = [], []
         for i in range(n):
             name = self.lib.pcx_table_name(i)
             a = self.tables[name.decode()]
             assert a.itemsize == self.lib.pcx_table_elem_size(i), name
             self._keep.append(a)
+            self._table_names.append(name)
             arr[i] = _Table(name, a.ctypes.data_as(ctypes.c_void_p), a.nbytes)
         for k, (name, a) in enumerate(extra):
             a = np.ascontiguousarray(a, dtype=np.int64)
             self._keep.append(a)
+            self._table_names.append(name)
             arr[n + k] = _Table(name, a.ctypes.data_as(ctypes.c_void_p), a.nbytes)
         n += len(extra)
         self._header = header.encode()
-        spec = _Spec(device=self.device, threads=self.threads, batch=self.batch,
-                     num_tiles=S.num_tiles, nvmax=S.NVMAX,
-                     n_border=len(S.border_grp), bv_size=S.bv_size,
-                     nred_max=max([l.nred for l in layouts] + [1]),
-                     btab_len=len(S.btab),
-                     reserved=self._min_blocks(min_blocks, S),
-                     num_x=S.num_x, num_c=S.num_c, num_dy=S.num_dy,
-                     nnz_g=S.nnz_g, nnz_h=S.nnz_h, smem_bytes=self.smem,
-                     problem_header=self._header, num_tables=n, tables=arr)
-        h = ctypes.c_void_p()
-        rc = self.lib.pcx_create(ctypes.byref(spec), ctypes.byref(h))
-        if rc != 0:
-            raise PcxError(f"pcx_create failed ({rc}): "
-                           f"{self.lib.pcx_last_error(None).decode(errors='replace')}")
-        self.h = h
+        self._spec_fields = dict(
+            threads=self.threads, batch=self.batch, num_tiles=S.num_tiles, nvmax=S.NVMAX,
+            n_border=len(S.border_grp), bv_size=S.bv_size,
+            nred_max=max([l.nred for l in layouts] + [1]), btab_len=len(S.btab),
+            reserved=self._min_blocks(min_blocks, S),
+            num_x=S.num_x, num_c=S.num_c, num_dy=S.num_dy,
+            nnz_g=S.nnz_g, nnz_h=S.nnz_h, smem_bytes=self.smem)
+        self._tables_arr = arr
+        return _Spec(device=self.device, problem_header=self._header, num_tables=n,
+                     tables=arr, **self._spec_fields)
 
     @staticmethod
     def _min_blocks(min_blocks, S):
@@ -410,6 +430,34 @@ class Engine:
         self._check(self.lib.pcx_set_scaling(
             self.h, _ptr(ps), ps.size, _ptr(gs), gs.size, _ptr(bc), bc.size,
             _ptr(pt), pt.size), "pcx_set_scaling")
+
+    def save_spec(self, path):
+        """Write everything ``pcx_create`` and ``pcx_set_scaling`` were given into one
+        file a compiled host opens with ``pcx_create_from_file`` (``include/pcx.h``
+        documents the layout): the symbolic problem definition stays in Python, as in
+        the reference, but the process that SOLVES needs no Python."""
+        f = self._spec_fields
+
+        def block(b):
+            return b + b"\0" * (-len(b) % 8)
+        out = [b"PCXSPEC1",
+               block(np.array([f["threads"], f["batch"], f["num_tiles"], f["nvmax"],
+                               f["n_border"], f["bv_size"], f["nred_max"], f["btab_len"],
+                               f["reserved"], len(self._keep)], dtype="<i4").tobytes()),
+               np.array([f["num_x"], f["num_c"], f["num_dy"], f["nnz_g"], f["nnz_h"],
+                         f["smem_bytes"]], dtype="<i8").tobytes()]
+        text = self._header + b"\0"
+        out += [np.int64(len(text)).tobytes(), block(text)]
+        for name, a in zip(self._table_names, self._keep):
+            nm = name + b"\0"
+            out += [np.int64(len(nm)).tobytes(), block(nm),
+                    np.int64(a.nbytes).tobytes(), block(a.tobytes())]
+        scal = getattr(self, "_scal", None) or [np.zeros(0)] * 4
+        out.append(np.array([a.size for a in scal], dtype="<i8").tobytes())
+        out += [np.ascontiguousarray(a, dtype="<f8").tobytes() for a in scal]
+        with open(path, "wb") as fh:
+            fh.write(b"".join(out))
+        return path
 
     # -- host-space convenience (numpy in / numpy out) ---------------------
     def eval_host(self, what, x, lam=None, sigma=None):

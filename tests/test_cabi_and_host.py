@@ -169,3 +169,108 @@ def test_backend_symbol_primitives():
     assert J == b.ir.J and J.free_symbols <= set(b.ir.point_symbols)
     with pytest.raises(ValueError, match="not defined"):
         b.substitute_pycollo_sym(sym.Symbol("nobody_defined_me") + 1, 0)
+
+
+# ---- a compiled host without Python in the process (pcx_create_from_file) ----------------
+
+def _build_tnlp_host(tmp_path):
+    import subprocess
+    exe = tmp_path / "tnlp_host"
+    libdir = os.path.join(ROOT, "pycollo_b200")
+    res = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", f"-I{os.path.join(ROOT, 'include')}",
+                          os.path.join(ROOT, "examples", "tnlp_host.cpp"), f"-L{libdir}", "-lpcx",
+                          f"-Wl,-rpath,{libdir}", "-o", str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    return exe
+
+
+def test_spec_file_is_parsed_and_bad_files_are_rejected(tmp_path):
+    """``Engine.write_spec`` -> ``pcx_create_from_file``: a well-formed file gets as far as
+    the device (PCX_OK with a GPU, PCX_ECUDA 'no CPU fallback' without one); unreadable,
+    foreign, truncated and over-long files are PCX_EINVAL with a message."""
+    from helpers import build_case
+    low, _, scal = build_case(examples.brachistochrone(), "lobatto", 10, 4, oracle=False)
+    path = str(tmp_path / "br.pcxspec")
+    E.Engine.write_spec(path, low.S, low.layouts, low.header, scal)
+    lib = E.load_library()
+    h = ctypes.c_void_p()
+    rc = lib.pcx_create_from_file(path.encode(), 0, ctypes.byref(h))
+    if rc == 0:
+        n = ctypes.c_int64()
+        lib.pcx_sizes(h, ctypes.byref(n), None, None, None, None, None)
+        assert n.value == low.S.num_x
+        lib.pcx_destroy(h)
+    else:
+        assert rc == -2 and b"no CPU fallback" in lib.pcx_last_error(None)
+    data = open(path, "rb").read()
+    cases = {"missing": None, "magic": b"NOTASPEC" + data[8:], "short": data[:len(data) // 2 // 8 * 8],
+             "odd": data[:-3], "long": data + b"\0" * 8, "empty": b""}
+    for name, blob in cases.items():
+        q = str(tmp_path / f"{name}.pcxspec")
+        if blob is not None:
+            open(q, "wb").write(blob)
+        assert lib.pcx_create_from_file(q.encode(), 0, ctypes.byref(h)) == -1, name
+        assert not h.value
+        assert len(lib.pcx_last_error(None)) > 8
+    assert lib.pcx_create_from_file(None, 0, ctypes.byref(h)) == -1
+
+
+def test_tnlp_host_example_compiles_against_the_c_header(tmp_path):
+    """include/pcx.h is consumable from C++ and the TNLP-shaped host links against libpcx.so."""
+    exe = _build_tnlp_host(tmp_path)
+    import subprocess
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 2 and "usage" in res.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["brachistochrone", "multiphase_sliding_mass"])
+def test_compiled_host_evaluates_without_python(name, tmp_path):
+    """The C++ TNLP-shaped host (examples/tnlp_host.cpp) creates the engine from a spec
+    file and calls every callback; results equal the Python-created engine's bit for bit,
+    in the row-major / lower-triangular order a cyipopt / IPOPT host is given."""
+    import subprocess
+    from helpers import build_case
+    low, _, scal = build_case(getattr(examples, name)(), "lobatto", 10, 4, oracle=False)
+    S = low.S
+    eng = E.Engine(S, low.layouts, low.header)
+    eng.set_scaling(*scal)
+    spec = str(tmp_path / "p.pcxspec")
+    eng.save_spec(spec)
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0.1, 0.4, S.num_x)
+    lam = rng.standard_normal(S.num_c)
+    x.tofile(tmp_path / "x.bin")
+    lam.tofile(tmp_path / "lam.bin")
+    exe = _build_tnlp_host(tmp_path)
+    res = subprocess.run([str(exe), spec, str(tmp_path / "x.bin"), str(tmp_path / "lam.bin"),
+                          str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    raw = open(tmp_path / "out.bin", "rb").read()
+    n, m, nj, nh = np.frombuffer(raw, dtype=np.int64, count=4)
+    assert (n, m, nj, nh) == (S.num_x, S.num_c, S.nnz_g, S.nnz_h)
+    off = 32
+
+    def take(dtype, count):
+        nonlocal off
+        a = np.frombuffer(raw, dtype=dtype, count=int(count), offset=off)
+        off += a.nbytes
+        return a
+    f = take(np.float64, 1)[0]
+    grad, g = take(np.float64, n), take(np.float64, m)
+    jr, jc, jv = take(np.int32, nj), take(np.int32, nj), take(np.float64, nj)
+    hr, hc, hv = take(np.int32, nh), take(np.int32, nh), take(np.float64, nh)
+    assert off == len(raw)
+    # the same three launches the host makes (same compiled variants => same bits)
+    ref = eng.eval_host(E.EVAL_F | E.EVAL_GRAD | E.EVAL_C, x)
+    ref.update(eng.eval_host(E.EVAL_JAC, x))
+    ref.update(eng.eval_host(E.EVAL_HESS, x, lam=lam, sigma=0.75))
+    rj, cj, pj = eng.structure_jac("row_major")
+    rh, ch, ph = eng.structure_hess("tril_row_major")
+    assert f == ref["f"][0]
+    assert np.array_equal(grad, ref["grad"][0]) and np.array_equal(g, ref["c"][0])
+    assert np.array_equal(jr, rj) and np.array_equal(jc, cj)
+    assert np.array_equal(hr, rh) and np.array_equal(hc, ch)
+    assert np.all(hr >= hc)                                           # lower triangle
+    assert np.array_equal(jv, ref["jac"][0][pj])
+    assert np.array_equal(hv, ref["hess"][0][ph])
