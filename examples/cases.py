@@ -22,6 +22,9 @@ GOLDEN_CASES = {
     "free_flying_robot_lobatto": ("free_flying_robot", dict(quadrature_method="lobatto"), SMALL),
     "multiphase_lobatto": ("multiphase_sliding_mass", dict(num_phases=3), SMALL),
     "shuttle_lobatto": ("space_shuttle_reentry", dict(quadrature_method="lobatto"), SMALL),
+    "free_flying_robot_radau": ("free_flying_robot", dict(quadrature_method="radau"), SMALL),
+    "multiphase_radau": ("multiphase_sliding_mass", dict(num_phases=3, quadrature_method="radau"), RAGGED),
+    "shuttle_radau": ("space_shuttle_reentry", dict(quadrature_method="radau"), SMALL),
     "double_pendulum_lobatto": ("double_pendulum", {}, None),
     "delta_iii_lobatto": ("delta_iii_launch_vehicle", {},
                           dict(number_mesh_sections=2, mesh_section_sizes=None,

@@ -291,7 +291,7 @@ def space_shuttle_reentry(quadrature_method="lobatto", api=None):
     return problem
 
 
-def multiphase_sliding_mass(num_phases=3, api=None):
+def multiphase_sliding_mass(num_phases=3, quadrature_method="lobatto", api=None):
     """``tests/integration/test_multiphase.py:25-75``: unit mass slid from 0 to 1,
     split in phases linked by endpoint constraints on velocity and time."""
     x, v, f = sym.symbols("x v f")
@@ -322,6 +322,7 @@ def multiphase_sliding_mass(num_phases=3, api=None):
         problem.endpoint_constraints = cons
         problem.bounds.endpoint_constraints = [[0, 0]] * len(cons)
     problem.objective_function = problem.phases[-1].final_time_variable
+    problem.settings.quadrature_method = quadrature_method
     return problem
 
 

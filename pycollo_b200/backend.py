@@ -40,8 +40,10 @@ from .symbolic import build_ir
 NlpResult = SimpleNamespace
 
 
-def lower_problem(ocp, meshes=None, **structure_kwargs):
-    """Symbolic lowering + structure + generated header for one mesh."""
+def lower_problem(ocp, meshes=None, share_bodies=None, **structure_kwargs):
+    """Symbolic lowering + structure + generated header for one mesh.  ``share_bodies``:
+    phases whose expression bodies differ in literals only share one instantiation of
+    the tile function (``codegen.share_groups``; None = the default, on)."""
     ir = build_ir(ocp)
     # Settings.derivative_level == 1: first derivatives only -- no Hessian program is
     # generated, compiled or exposed (the reference's live backend ignores the
@@ -55,7 +57,7 @@ def lower_problem(ocp, meshes=None, **structure_kwargs):
     S = NLPStructure(ir, pds, ptd, meshes,
                      prune=ocp.settings.prune_zero_quadrature_coefficients,
                      **structure_kwargs)
-    header, layouts = codegen.generate(ir, pds, ptd, S)
+    header, layouts = codegen.generate(ir, pds, ptd, S, share=share_bodies)
     return SimpleNamespace(ir=ir, pds=pds, ptd=ptd, S=S, header=header,
                            layouts=layouts, meshes=meshes)
 

@@ -332,3 +332,22 @@ def test_no_write_outside_the_output_arrays(name, K, nodes, kw):
     for k in ("f", "grad", "c", "dy", "jac", "hess"):   # and every slot was written
         assert not bool((views[k] == SENT).any()), f"unwritten slot in {k}"
         assert bool(torch.isfinite(views[k]).all()), k
+
+
+@pytest.mark.parametrize("name,K", [("delta_iii_launch_vehicle", 12), ("multiphase_sliding_mass", 9)])
+def test_shared_expression_bodies_change_no_bit(name, K):
+    """Phases that differ in literals only run ONE instantiation of the tile function
+    (``codegen.share_groups``): same operations on the same doubles, so every output
+    equals the one-instantiation-per-phase kernel's bit for bit."""
+    low_s, _, scal = build_case(getattr(examples, name)(), "lobatto", K, 4, oracle=False)
+    low_u, _, _ = build_case(getattr(examples, name)(), "lobatto", K, 4, oracle=False,
+                             share_bodies=False)
+    assert any(lay.leader != q for q, lay in enumerate(low_s.layouts))
+    assert all(lay.leader == q and not lay.kc for q, lay in enumerate(low_u.layouts))
+    rng = np.random.default_rng(11)
+    x = rng.uniform(0.1, 0.4, low_s.S.num_x)
+    lam = rng.standard_normal(low_s.S.num_c)
+    a = make_engine(low_s, scal).eval_host(ALL, x, lam, 0.6)
+    b = make_engine(low_u, scal).eval_host(ALL, x, lam, 0.6)
+    for k in b:
+        assert np.array_equal(a[k], b[k]), k
