@@ -33,6 +33,9 @@ One *step* = one evaluation of (G values, H values) for one synthetic iterate
   ~10^6 nodes) split over the N ranks by tile ranges, border values exchanged
   inside the kernel over NVLink peer memory; checked in-process against the
   unsharded evaluation, timed as max over ranks.
+* ``config4_1gpu`` (N = 1 only, informational): the same Delta III mesh on ONE GPU --
+  the large-expression-body kernel (four phases sharing one body), ms per fused
+  G+H evaluation and its fraction of the measured HBM rate (``--no-config4`` skips it).
 * ``--impl reference``: the reference's CPU implementation of this path.  The
   live reference (CasADi) cannot be installed here (no casadi/pyproprop wheel,
   no network), so this arm times the oracle port with every host
@@ -339,6 +342,45 @@ def batched_rate(low, scal, E, torch, dev, stream, alg_bytes, peak, batch=8, ste
             "note": "same kernel, 8 independent iterates per launch (grid.y); informational"}
 
 
+def config4_one_gpu(args, torch, E, dev, peak):
+    """BASELINE config 4 on ONE GPU (informational, N = 1 only): Delta III, 4 phases,
+    ~10^6 collocation nodes, fused G+H, device-resident, the launches enqueued by one
+    C call behind a stream gate and timed by CUDA events on the launch stream.  Two
+    output sets of 1.4 GB each alternate (>> L2)."""
+    from examples import problems
+    from examples.cases import lower_case
+    K = args.strong_sections
+    what = E.EVAL_JAC | E.EVAL_HESS
+    low, _, scal = lower_case(problems.delta_iii_launch_vehicle(), "lobatto", K, 4, seed=0)
+    S = low.S
+    eng = E.Engine(S, low.layouts, low.header, device=dev.index or 0, structure=False)
+    eng.set_scaling(*scal)
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = 0.1 + 0.3 * torch.rand(S.num_x, dtype=torch.float64, device=dev, generator=g)
+    lam = torch.randn(S.num_c, dtype=torch.float64, device=dev, generator=g)
+    sets = [dict(x=x, lam=lam, jac=torch.empty(S.nnz_g, dtype=torch.float64, device=dev),
+                 hess=torch.empty(S.nnz_h, dtype=torch.float64, device=dev)) for _ in range(2)]
+    cargs = eng.make_args(sets)
+    st = torch.cuda.current_stream().cuda_stream
+    steps = 10
+    eng.eval_many(what, cargs, 3, stream=st, gate=False, timed=False)
+    torch.cuda.synchronize()
+    ms = eng.eval_many(what, cargs, steps, stream=st, gate=True, timed=True) / steps
+    alg = 8 * (S.num_x + S.nnz_g) + 8 * (S.num_x + S.num_c + S.nnz_h)
+    info = eng.variant_info(what)
+    out = {"workload": "delta_iii_launch_vehicle, 4 phases x %d sections x 4 nodes = %d collocation "
+                       "nodes, one GPU" % (K, int(sum(t_.N for t_ in S.ph))),
+           "num_x": int(S.num_x), "nnz_G": int(S.nnz_g), "nnz_H": int(S.nnz_h),
+           "tiles": int(S.num_tiles), "threads": int(S.threads),
+           "phases_sharing_one_body": [int(lay.leader) for lay in low.layouts],
+           "ms_per_eval": ms, "evals_per_s": 1e3 / ms, "steps": steps,
+           "algorithmic_bytes_per_launch": int(alg), "achieved_GBs": alg / ms / 1e6,
+           "frac": alg / (ms * 1e-3) / 1e9 / peak, "kernel": info}
+    del eng, sets, cargs, x, lam
+    torch.cuda.empty_cache()
+    return out
+
+
 def strong_scaling(args, torch, dist, E, rank, world, local_rank):
     """BASELINE config 4 under the driver's own launch: ONE Delta III mesh (4 phases,
     ~10^6 nodes) split over the ranks by tile ranges, border values exchanged inside
@@ -596,8 +638,15 @@ def run_cuda(args):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         amortised = None
         cpu = None
+        config4 = None
         if world == 1:
             amortised = batched_rate(low, scal, E, torch, dev, stream, alg_bytes, peak)
+            if not args.no_config4:
+                try:
+                    config4 = config4_one_gpu(args, torch, E, dev, peak)
+                    launches += 13
+                except Exception as exc:              # informational: never hides the headline
+                    config4 = {"error": repr(exc)[:300]}
             if not args.no_cpu_baseline:
                 cpu = cpu_baseline_block()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
@@ -642,6 +691,8 @@ def run_cuda(args):
                 "amortised": amortised}
         if strong is not None:
             line["strong"] = strong
+        if config4 is not None:
+            line["config4_1gpu"] = config4
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -655,6 +706,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true",
+                    help="skip the informational Delta III 10^6-node leg of a one-GPU run")
     ap.add_argument("--no-strong", action="store_true",
                     help="skip the mesh-sharded (config 4) leg of a multi-GPU run")
     ap.add_argument("--strong-sections", type=int, default=STRONG_K,

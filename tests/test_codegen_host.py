@@ -133,3 +133,29 @@ def test_generated_bodies_match_sympy_on_the_host(name, tmp_path):
             assert g.shape == ref.shape
             scale = np.maximum(np.abs(ref), 1e-3 * np.abs(ref).max() + 1e-300)
             assert np.max(np.abs(g - ref) / scale) <= 1e-11, (name, ip)
+
+
+def test_share_groups_on_text():
+    """``codegen.share_groups``: same signature => one leader; only the literals that
+    differ become ``kc`` reads (one slot per distinct value tuple); identifiers with
+    digits, template arguments and integers are not literals."""
+    from pycollo_b200.codegen import share_groups, _LITERAL
+    body = ("const double w_0 = {a}*v10 + 1.0;\n"
+            "o.template D1V<3>(w_0*{b} - 2.5e-3*mh1);\n"
+            "o.template F<0>({a}*w_0/{c});")
+    bodies = [body.format(a="4854100.0", b="1723.25", c="3.0"),
+              body.format(a="2968600.0", b="1044.5", c="3.0"),
+              "const double w_0 = 2.0*v10;\no.template F<0>(w_0);",
+              body.format(a="1083100.0", b="366.0", c="3.0")]
+    sig = [("dims", _LITERAL.sub("#", b)) for b in bodies]
+    leader, kc, shared = share_groups(sig, bodies)
+    assert leader == [0, 0, 2, 0]
+    assert kc == [[4854100.0, 1723.25], [2968600.0, 1044.5], [], [1083100.0, 366.0]]
+    assert list(shared) == [0]
+    assert shared[0] == ("const double w_0 = kc[0]*v10 + 1.0;\n"
+                         "o.template D1V<3>(w_0*kc[1] - 2.5e-3*mh1);\n"
+                         "o.template F<0>(kc[0]*w_0/3.0);")
+    # different dimension tables never share, whatever the text
+    leader, kc, shared = share_groups([("a", "x"), ("b", "x")], ["1.0", "2.0"])
+    assert leader == [0, 1] and kc == [[], []] and not shared
+    assert _LITERAL.findall("v10 w_12 F<3> 1.5 2e-3 7.0e+2 x1.5 3") == ["1.5", "2e-3", "7.0e+2"]
