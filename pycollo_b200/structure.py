@@ -806,6 +806,19 @@ class NLPStructure:
                 # shared memory the limit (227 KB per SM, ~8 KB of static + tables)
                 res = resident_ctas(T)
                 stage = self.bytes_per_node(pd) * cap
+                nout = (len(pd.fns) + len(pd.d1v) + len(pd.d1s) + len(pd.h2vv) + len(pd.h2vs)
+                        + len(pd.h2ss) + len(pd.htv) + len(pd.hts))
+                if nout > 40 and len(pd.h2vv) >= 16:
+                    # two-pass node phase (engine.smem_bytes): also the multipliers with
+                    # their halo and, where the vacated first-derivative staging is too
+                    # small for it, the rest of the Hessian staging.  Without this Delta
+                    # III was tiled for 4 CTAs per SM while 3 are resident: a rank of an
+                    # 8-way sharded mesh ran 2.67 waves instead of 3 whole, smaller ones
+                    nds = sum(1 for e, _ in pd.d1s if pd.fam[e] == "d")
+                    ss = cap // 3 + 1
+                    region = (len(pd.d1v) + nds) * (cap | 1) + len(pd.d1v) * (ss + 1)
+                    stage = 8 * ((pd.NY + len(pd.d1v) + nds) * (cap | 1) + len(pd.d1v) * (ss + 1)
+                                 + pd.NY * (cap + 24) + max(0, len(pd.h2vv) * T - region))
                 if stage > 40 * 1024:
                     res = max(1, min(res, (227 * 1024) // (stage + 8 * 1024)))
                 if tiles_per_sm:
