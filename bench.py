@@ -395,8 +395,8 @@ def strong_scaling(args, torch, dist, E, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     what = E.EVAL_JAC | E.EVAL_HESS
     ocp = problems.delta_iii_launch_vehicle()
-    # the tiling is built for world x 148 SMs, so a rank's share of the tiles is a
-    # whole number of waves of ITS 148 SMs
+    # the tiling is built for world x 148 SMs: the tile count is chosen for a rank's own
+    # 148 SMs and its share of the mesh
     low, _, scal = lower_case(ocp, "lobatto", K, 4, seed=0, sm_count=148 * world)
     S = low.S
     eng = E.Engine(S, low.layouts, low.header, device=local_rank, structure=False)

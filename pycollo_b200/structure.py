@@ -808,22 +808,20 @@ class NLPStructure:
                 stage = self.bytes_per_node(pd) * cap
                 nout = (len(pd.fns) + len(pd.d1v) + len(pd.d1s) + len(pd.h2vv) + len(pd.h2vs)
                         + len(pd.h2ss) + len(pd.htv) + len(pd.hts))
-                if nout > 40 and len(pd.h2vv) >= 16:
-                    # two-pass node phase (engine.smem_bytes): also the multipliers with
-                    # their halo and, where the vacated first-derivative staging is too
-                    # small for it, the rest of the Hessian staging.  Without this Delta
-                    # III was tiled for 4 CTAs per SM while 3 are resident: a rank of an
-                    # 8-way sharded mesh ran 2.67 waves instead of 3 whole, smaller ones
-                    nds = sum(1 for e, _ in pd.d1s if pd.fam[e] == "d")
-                    ss = cap // 3 + 1
-                    region = (len(pd.d1v) + nds) * (cap | 1) + len(pd.d1v) * (ss + 1)
-                    stage = 8 * ((pd.NY + len(pd.d1v) + nds) * (cap | 1) + len(pd.d1v) * (ss + 1)
-                                 + pd.NY * (cap + 24) + max(0, len(pd.h2vv) * T - region))
+                # Large bodies in the two-pass node phase (engine.smem_bytes; Delta III,
+                # shuttle): a tile costs ~4 us of table prologue whatever its size and the
+                # CTAs of an SM drift apart within a wave or two, so whole waves buy
+                # nothing and every extra tile costs -- measured on Delta III, 10^6 nodes
+                # (profiles/r02_d3_tiling.txt): 54 tiles per SM 0.338 ms against 56 at
+                # 0.343; a rank of an 8-way sharded mesh 7 per SM 52.0 us, 8: 52.3, 9 (three
+                # whole waves of the 3 resident CTAs): 57.7; 4-way 14: 88.9, 16: 97.4.
+                # They get the fewest tiles the node cap allows.
+                two_pass = nout > 40 and len(pd.h2vv) >= 16
                 if stage > 40 * 1024:
                     res = max(1, min(res, (227 * 1024) // (stage + 8 * 1024)))
                 if tiles_per_sm:
                     m = max(m, int(tiles_per_sm))
-                elif m > res:
+                elif m > res and not two_pass:
                     m = -(-m // res) * res                             # whole waves
                 want = max(want, int(round(m * sm_count * share)))
             want = min(want, t.K)
