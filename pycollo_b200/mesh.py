@@ -59,18 +59,21 @@ class PhaseMeshData:
 
     def __init__(self, quadrature: Quadrature, phase_mesh: PhaseMesh,
                  collocation_points_min=2, collocation_points_max=10):
-        nodes = phase_mesh.number_mesh_section_nodes
-        for k, n in enumerate(nodes):
+        nodes = np.asarray(phase_mesh.number_mesh_section_nodes)
+        low = np.flatnonzero(nodes < collocation_points_min)
+        high = np.flatnonzero(nodes > collocation_points_max)
+        first = min([int(a[0]) for a in (low, high) if a.size], default=None)
+        if first is not None:
+            n, k = nodes[first], first
             if n < collocation_points_min:
                 raise ValueError(
                     f"The number of collocation points, {n}, in mesh section "
                     f"{k} must be greater than or equal to "
                     f"{collocation_points_min}.")
-            if n > collocation_points_max:
-                raise ValueError(
-                    f"The number of collocation points, {n}, in mesh section "
-                    f"{k} must be less than or equal to "
-                    f"{collocation_points_max}.")
+            raise ValueError(
+                f"The number of collocation points, {n}, in mesh section "
+                f"{k} must be less than or equal to "
+                f"{collocation_points_max}.")
         self.quadrature = quadrature
         self.K = phase_mesh.number_mesh_sections
         self.N_K = nodes.copy()
@@ -81,28 +84,42 @@ class PhaseMeshData:
             bounds.append(bounds[-1] + (TAU_F - TAU_0) * frac)
         bounds = np.array(bounds)
 
-        pieces = []
-        for k in range(self.K):
-            pts = quadrature.quadrature_point(
-                int(nodes[k]), domain=[bounds[k], bounds[k + 1]])
-            pieces.append(pts[:-1])
-        self.tau = np.concatenate(pieces + [np.array([TAU_F])])
-        self.h = np.diff(self.tau)
-        self.N = int(self.tau.size)
+        # Sections of one order are mapped together (10^6-node meshes: a Python loop over
+        # the sections took seconds per phase); element by element the arithmetic is the
+        # per-section statement of pycollo/mesh.py:283-326 -- stretch * points + shift,
+        # weights * h_k -- so the arrays equal the loop's (and the reference's) bit for bit.
         self.mesh_index_boundaries = np.concatenate(
             [[0], np.cumsum(nodes - 1)]).astype(np.int64)
+        start = self.mesh_index_boundaries[:-1]
+        self.N = int(self.mesh_index_boundaries[-1]) + 1
+        self.tau = np.empty(self.N)
+        self.tau[-1] = TAU_F
+        groups = [(int(n), np.flatnonzero(nodes == n)) for n in np.unique(nodes)]
+        for n, idx in groups:
+            pts = quadrature.quadrature_point(n)
+            stretch = 0.5 * (bounds[idx + 1] - bounds[idx])
+            shift = 0.5 * (bounds[idx] + bounds[idx + 1])
+            mapped = stretch[:, None] * pts[None, :] + shift[:, None]
+            self.tau[start[idx][:, None] + np.arange(n - 1)[None, :]] = mapped[:, :-1]
+        self.h = np.diff(self.tau)
         self.h_K = np.diff(self.tau[self.mesh_index_boundaries])
         self.num_c_defect_per_y = int(self.mesh_index_boundaries[-1])
 
-        # quadrature row and per-section dense integration blocks
+        # quadrature row (a shared end node receives two contributions: their sum does not
+        # depend on the order); the dense per-section integration blocks are formed on demand
         self.W_matrix = np.zeros(self.N)
-        self.I_blocks = []
-        for k in range(self.K):
-            n = int(nodes[k])
-            b = int(self.mesh_index_boundaries[k])
-            hk = self.h_K[k]
-            self.I_blocks.append(quadrature.A_matrix(n) * hk)
-            self.W_matrix[b:b + n] += quadrature.quadrature_weight(n) * hk
+        for n, idx in groups:
+            contrib = quadrature.quadrature_weight(n)[None, :] * self.h_K[idx][:, None]
+            np.add.at(self.W_matrix, start[idx][:, None] + np.arange(n)[None, :], contrib)
+        self._I_blocks = None
+
+    @property
+    def I_blocks(self):
+        """Per-section integration blocks ``ButcherRows(N_k) * h_k`` (``pycollo/mesh.py:300``)."""
+        if self._I_blocks is None:
+            self._I_blocks = [self.quadrature.A_matrix(int(n)) * hk
+                              for n, hk in zip(self.N_K, self.h_K)]
+        return self._I_blocks
 
     # -- CSR views with the reference's attribute names -----------------
     @property
@@ -149,7 +166,7 @@ class PhaseMeshData:
         self.N = int(self.mesh_index_boundaries[-1]) + 1
         self.num_c_defect_per_y = self.N - 1
         self.h_K = np.asarray(h_K, dtype=np.float64)
-        self.I_blocks = [np.asarray(b, dtype=np.float64) for b in I_blocks]
+        self._I_blocks = [np.asarray(b, dtype=np.float64) for b in I_blocks]
         self.W_matrix = np.asarray(W_matrix, dtype=np.float64)
         self.tau = None if tau is None else np.asarray(tau, dtype=np.float64)
         self.h = None if tau is None else np.diff(self.tau)
