@@ -302,7 +302,7 @@ def generate(ir, phase_derivs, point_derivs, structure, share=None):
            "template <int P> struct PcxPhase;\n"]
     # the expression bodies (the expensive part: one sympy.cse program per phase), then
     # the phases that may share one
-    bodies = [_phase_body(pd, NS) for pd in phase_derivs]
+    bodies = [_cached(pd, ("body", NS), lambda pd=pd: _phase_body(pd, NS)) for pd in phase_derivs]
     leader, kcs, shared_body = list(range(P)), [[] for _ in range(P)], {}
     if share and P > 1:
         sig = [(_phase_dims(pd, PhaseLayout(pd, ph.t_needed[0], ph.t_needed[1], 0, 0)),
@@ -330,9 +330,18 @@ def generate(ir, phase_derivs, point_derivs, structure, share=None):
     pb0 = layouts[0].pb
     out.append(f"#define PCX_PB_T0X {pb0['T0X']}\n#define PCX_PB_TFX {pb0['TFX']}\n"
                f"#define PCX_PB_TILE0 {pb0['TILE0']}\n#define PCX_PB_TILE1 {pb0['TILE1']}\n")
-    out.append(_point_function(point_derivs, NB))
+    out.append(_cached(point_derivs, ("point", NB), lambda: _point_function(point_derivs, NB)))
     src = "".join(out)
     return src, layouts
+
+
+def _cached(obj, key, make):
+    """Generated text kept on the (mesh-independent, cached: derivs.analyse_phase) analysis
+    object it was generated from, so that a new mesh of the same problem re-uses it."""
+    store = obj.__dict__.setdefault("_generated", {})
+    if key not in store:
+        store[key] = make()
+    return store[key]
 
 
 def _phase_dims(pd, lay):

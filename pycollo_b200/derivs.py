@@ -59,9 +59,35 @@ class PhaseDerivs:
                  [(e, j + self.NV) for e, j in self.d1s]) if aa == a}
 
 
+# The analysis depends on the symbolic problem only, never on the mesh: a mesh refinement
+# (a new Iteration, a new ph-mesh error engine: two lowerings per mesh iteration) finds it
+# here instead of differentiating everything again (Delta III: ~1 s per phase, the cse of
+# the code generator another 1.5 s).  Keys are the (immutable, hashable) sympy expressions
+# themselves; results are read-only by convention.
+_CACHE_MAX = 64
+_PHASE_CACHE: dict = {}
+_POINT_CACHE: dict = {}
+
+
+def _remember(cache, key, make):
+    hit = cache.get(key)
+    if hit is None:
+        if len(cache) >= _CACHE_MAX:
+            cache.pop(next(iter(cache)))
+        hit = cache[key] = make()
+    return hit
+
+
 def analyse_phase(ph, s_syms, second=True) -> PhaseDerivs:
     """``second=False`` (``Settings.derivative_level == 1``): no second derivatives
     are formed, so no Hessian program is generated or compiled."""
+    key = (ph.index, tuple(ph.y), tuple(ph.u), tuple(sym.sympify(e) for e in ph.f),
+           tuple(sym.sympify(e) for e in ph.p), tuple(sym.sympify(e) for e in ph.g),
+           tuple(s_syms), bool(second))
+    return _remember(_PHASE_CACHE, key, lambda: _analyse_phase(ph, s_syms, second))
+
+
+def _analyse_phase(ph, s_syms, second) -> PhaseDerivs:
     v = list(ph.y) + list(ph.u)
     allv = v + list(s_syms)
     fns = list(ph.f) + list(ph.p) + list(ph.g)
@@ -118,6 +144,12 @@ class PointDerivs:
 
 
 def analyse_point(ir, second=True) -> PointDerivs:
+    key = (tuple(ir.point_symbols), sym.sympify(ir.J), tuple(sym.sympify(e) for e in ir.b),
+           bool(second))
+    return _remember(_POINT_CACHE, key, lambda: _analyse_point(ir, second))
+
+
+def _analyse_point(ir, second) -> PointDerivs:
     pts = list(ir.point_symbols)
     fns = [ir.J] + list(ir.b)
     d1, d1e, d2, pairs = [], [], [], set()

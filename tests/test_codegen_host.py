@@ -159,3 +159,23 @@ def test_share_groups_on_text():
     leader, kc, shared = share_groups([("a", "x"), ("b", "x")], ["1.0", "2.0"])
     assert leader == [0, 1] and kc == [[], []] and not shared
     assert _LITERAL.findall("v10 w_12 F<3> 1.5 2e-3 7.0e+2 x1.5 3") == ["1.5", "2e-3", "7.0e+2"]
+
+
+def test_symbolic_analysis_and_bodies_are_reused_across_meshes():
+    """A mesh refinement re-lowers the same problem on another mesh: the derivative
+    analysis and the generated bodies depend on the symbolic problem only, are found in
+    the cache (same objects), and the header -- hence the compiled kernel -- is the same;
+    another problem, or another derivative level, is not confused with it."""
+    from pycollo_b200 import derivs
+    low_a, _, _ = build_case(examples.space_shuttle_reentry(), "lobatto", 5, 4, oracle=False)
+    low_b, _, _ = build_case(examples.space_shuttle_reentry(), "lobatto", 9, 6, oracle=False)
+    assert low_a.pds[0] is low_b.pds[0] and low_a.ptd is low_b.ptd
+    assert low_a.header == low_b.header
+    assert low_a.S.num_x != low_b.S.num_x
+    low_c, _, _ = build_case(examples.free_flying_robot(), "lobatto", 5, 4, oracle=False)
+    assert low_c.pds[0] is not low_a.pds[0] and low_c.header != low_a.header
+    ocp = examples.space_shuttle_reentry()
+    ocp.settings.derivative_level = 1
+    low_d, _, _ = build_case(ocp, "lobatto", 5, 4, oracle=False)
+    assert low_d.pds[0] is not low_a.pds[0] and not low_d.pds[0].h2vv and low_a.pds[0].h2vv
+    assert len(derivs._PHASE_CACHE) <= derivs._CACHE_MAX
