@@ -688,7 +688,29 @@ class Cuda:
         J = float(np.asarray(sol["f"]).ravel()[0]) if "f" in sol else None
         return Solution(iteration, x, J)
 
-    def solve_nlp(self):
-        raise NotImplementedError(
-            "No host NLP solver (IPOPT) is available in this environment; "
-            "use Cuda.nlp_callbacks() with cyipopt - see INTEGRATION.md.")
+    def solve_nlp(self, callbacks=None, verbose=False):
+        """``backend.py:1807-1827``: solve the NLP of the current mesh iteration from its
+        scaled guess inside its scaled bounds; returns ``NlpResult(solution, info,
+        solve_time)`` with ``solution`` keyed like ``ca.nlpsol``'s output (``"x"``, ``"f"``,
+        ``"g"``, ``"lam_g"``, scaled basis).
+
+        The reference hands the callbacks to IPOPT.  Neither IPOPT nor cyipopt exists in
+        this image (attaching cyipopt: INTEGRATION.md), so the host solver is the built-in
+        interior-point Newton method (``ipnewton.py``) over the same cyipopt-style callback
+        object -- host linear algebra, as IPOPT's is; every value and derivative comes from
+        the CUDA callbacks.  ``callbacks``: another object with the same contract (tests)."""
+        from . import ipnewton
+        it = self._it()
+        cb = callbacks if callbacks is not None else self.nlp_callbacks("cyipopt")
+        settings = self.ocp.settings
+        t0 = timer()
+        res = ipnewton.solve(cb, it.guess_x_tilde, it.x_bnd_l, it.x_bnd_u, it.c_bnd_l,
+                             it.c_bnd_u, tol=float(settings.nlp_tolerance),
+                             max_iter=int(settings.max_nlp_iterations), verbose=verbose)
+        solve_time = timer() - t0
+        solution = {"x": res.x, "f": res.fun, "g": np.asarray(cb.constraints(res.x)),
+                    "lam_g": res.lam}
+        info = {"solver": "pycollo_b200.ipnewton", "success": res.success,
+                "iterations": res.nit, "kkt_error": res.kkt_error,
+                "constraint_violation": res.constr_violation}
+        return NlpResult(solution=solution, info=info, solve_time=solve_time)

@@ -436,13 +436,32 @@ class OptimalControlProblem:
         return self
 
     def solve(self, display_progress=False):
-        """Driving IPOPT is the host NLP solver's job.
+        """ONE mesh iteration of the reference's solve (``optimal_control_problem.py:
+        339-...``, ``iteration.py:474-526``): NLP solve from the guess -> processed
+        solution (``casadi_solution.py``) -> mesh-refinement error of the solved mesh
+        (``mesh_refinement.py:60-73``); sets ``nlp_result``, ``solution``,
+        ``mesh_refinement`` and ``mesh_tolerance_met`` and returns the solution.
 
-        No IPOPT/cyipopt/CasADi exists in this image, so the solve loop cannot
-        run here; the callbacks it would call are
-        ``problem._backend.nlp_callbacks()`` (cyipopt-style object).
+        The host NLP solver is the backend's (``Cuda.solve_nlp``: the built-in
+        interior-point method; IPOPT / cyipopt are absent from this image).  Building the
+        NEXT mesh from the errors and looping (Patterson-Rao re-meshing) is the
+        reference's control plane, outside this package's scope:
+        a caller that has it continues with ``_backend.new_mesh_iteration(mesh, guess)``.
         """
-        raise NotImplementedError(
-            "pycollo_b200 provides the NLP callback engine (backend='cuda'); "
-            "attach a host NLP solver through Cuda.nlp_callbacks() - see "
-            "INTEGRATION.md.")
+        if not getattr(self, "_is_initialised", False):
+            self.initialise()
+        backend = self._backend
+        iteration = backend.current_iteration
+        self.nlp_result = backend.solve_nlp(verbose=display_progress)
+        self.solution = backend.process_solution(iteration, self.nlp_result)
+        self.mesh_refinement = self.solution.refine_mesh()
+        worst = max([float(np.max(m)) for m in
+                     self.mesh_refinement.maximum_relative_mesh_errors if np.size(m)] + [0.0])
+        self.mesh_tolerance_met = bool(worst <= float(self.settings.mesh_tolerance))
+        if display_progress:
+            info = self.nlp_result.info
+            print(f"mesh iteration 0: J = {self.solution.objective:.12g} in "
+                  f"{info['iterations']} NLP iterations ({self.nlp_result.solve_time:.2f} s), "
+                  f"largest relative mesh error {worst:.3e} "
+                  f"(tolerance {float(self.settings.mesh_tolerance):.1e})")
+        return self.solution

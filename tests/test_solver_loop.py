@@ -73,3 +73,25 @@ def test_cuda_callbacks_solve_like_the_oracle(name, cuda_device):
     np.testing.assert_allclose(res.x, ref.x, atol=1e-7)
     if pin is not None:
         np.testing.assert_allclose(res.J_user, pin, rtol=rtol)
+
+
+def test_backend_solve_nlp_runs_the_builtin_solver():
+    """``Cuda.solve_nlp`` (``backend.py:1807-1827``): guess, bounds, tolerance and iteration
+    limit of the current mesh iteration handed to the built-in interior-point solver;
+    an ``NlpResult`` keyed like nlpsol's output comes back.  CPU: the callbacks are the
+    oracle's (the engine is deferred); the GPU test above drives the same solver with
+    the CUDA callbacks."""
+    ocp = problems.brachistochrone()
+    ocp.settings.defer_engine = True
+    ocp.initialise()
+    backend = ocp._backend
+    it = backend.mesh_iterations[0]
+    res = backend.solve_nlp(callbacks=OracleCallbacks(_oracle_for(ocp, it)))
+    assert res.info["solver"] == "pycollo_b200.ipnewton" and res.info["success"]
+    assert res.info["kkt_error"] <= ocp.settings.nlp_tolerance
+    assert res.solve_time > 0
+    sol = res.solution
+    assert sol["x"].shape == (it.S.num_x,) and sol["lam_g"].shape == (it.S.num_c,)
+    assert sol["g"].shape == (it.S.num_c,) and np.max(np.abs(sol["g"])) <= 1e-8
+    np.testing.assert_allclose(it.scaling.unscale_J(sol["f"]), 0.8243386694458454, rtol=1e-8)
+    assert np.all(sol["x"] >= it.x_bnd_l - 1e-12) and np.all(sol["x"] <= it.x_bnd_u + 1e-12)
