@@ -380,6 +380,7 @@ class NLPStructure:
         slot = 0
         self.g_border = []         # (slot, row, col, descriptor)
         g_rows_parts, g_cols_parts, g_slot_parts = [], [], []
+        g_thunks = []              # deferred pattern blocks: () -> (rows, cols, slots)
         words = []
         for ip, (ph, pd, mesh, t) in enumerate(zip(self.ir.phases, self.pd,
                                                    self.meshes, self.ph)):
@@ -434,32 +435,18 @@ class NLPStructure:
                         continue
                     ks = np.flatnonzero(t.sec_type_local == lt)
                     E = np.asarray(ents, dtype=np.int64)
-                    mloc, rk, idx, l, prev = E[:, 0], E[:, 1], E[:, 2], E[:, 3], E[:, 4]
-                    b_k = t.sec_node[ks][:, None]
-                    b_prev = t.sec_node[np.maximum(ks - 1, 0)][:, None]
-                    node = b_k + mloc[None, :]
-                    rows = np.where(
-                        rk[None, :] == 0,
-                        t.c_off + idx[None, :] * (N - 1)
-                        + np.where(prev[None, :] == 1, b_prev, b_k) + l[None, :],
-                        np.where(
-                            rk[None, :] == 1,
-                            t.c_off + NY * (N - 1) + idx[None, :] * N + node,
-                            np.where(rk[None, :] == 2,
-                                     t.c_off + NY * (N - 1) + NP * N + idx[None, :],
-                                     self.b_off + idx[None, :])))
-                    cols = t.x_off + a * N + node
-                    sl = t.gsec_ptr[a, ks][:, None] + np.arange(len(ents))[None, :]
-                    g_rows_parts.append(rows.ravel())
-                    g_cols_parts.append(cols.ravel())
-                    g_slot_parts.append(sl.ravel())
+                    # the (row, col, slot) triplets of these sections are formed when the
+                    # pattern is asked for (G_structure): at 10^6 nodes they are 10^8
+                    # entries that an evaluation-only engine never needs
+                    g_thunks.append(self._recipe_pattern(t, a, ks, E, NY, NP, N))
                     # endpoint (skip) entries go to the border map
                     for ie, ent in enumerate(ents):
                         if ent[9]:
-                            for kk, k_sec in enumerate(ks):
+                            for k_sec in ks:
                                 self.g_border.append(
-                                    (int(sl[kk, ie]), ("b_d1", int(ent[2]),
-                                                       int(cols[kk, ie]))))
+                                    (int(t.gsec_ptr[a, k_sec]) + ie,
+                                     ("b_d1", int(ent[2]),
+                                      int(t.x_off + a * N + t.sec_node[k_sec] + ent[0]))))
             # ---- border columns of this phase: q, then free t ----
             for i in range(NQ):
                 col = t.q_col + i
@@ -527,7 +514,7 @@ class NLPStructure:
         self.nnz_g = slot
         self.recipe_words = np.asarray(words, dtype=np.uint64)
         self.type_var_off = np.asarray(self.type_var_off, dtype=np.int32)
-        self._g_parts = (g_rows_parts, g_cols_parts, g_slot_parts)
+        self._g_parts = (g_rows_parts, g_cols_parts, g_slot_parts, g_thunks)
         self._G_rows = self._G_cols = None
 
     def G_constant_ranges(self, min_len=4096):
@@ -592,16 +579,48 @@ class NLPStructure:
                 slot += 1
         return slot
 
+    def _recipe_pattern(self, t, a, ks, E, NY, NP, N):
+        """Deferred (rows, cols, slots) of variable ``a``'s recipe entries ``E`` in the
+        sections ``ks`` of one type (vectorised per type)."""
+        b_off = self.b_off
+
+        def make():
+            mloc, rk, idx, l, prev = E[:, 0], E[:, 1], E[:, 2], E[:, 3], E[:, 4]
+            b_k = t.sec_node[ks][:, None]
+            b_prev = t.sec_node[np.maximum(ks - 1, 0)][:, None]
+            node = b_k + mloc[None, :]
+            rows = np.where(
+                rk[None, :] == 0,
+                t.c_off + idx[None, :] * (N - 1)
+                + np.where(prev[None, :] == 1, b_prev, b_k) + l[None, :],
+                np.where(
+                    rk[None, :] == 1,
+                    t.c_off + NY * (N - 1) + idx[None, :] * N + node,
+                    np.where(rk[None, :] == 2,
+                             t.c_off + NY * (N - 1) + NP * N + idx[None, :],
+                             b_off + idx[None, :])))
+            cols = t.x_off + a * N + node
+            sl = t.gsec_ptr[a, ks][:, None] + np.arange(E.shape[0])[None, :]
+            return rows.ravel(), cols.ravel(), sl.ravel()
+        return make
+
     def G_structure(self):
         if self._G_rows is None:
-            rp, cp, sp = self._g_parts
+            rp, cp, sp, thunks = self._g_parts
             rows = np.empty(self.nnz_g, dtype=np.int64)
             cols = np.empty(self.nnz_g, dtype=np.int64)
-            if self.nnz_g:
+            count = 0
+            if rp:
                 sl = np.concatenate(sp)
-                assert len(sl) == self.nnz_g, (len(sl), self.nnz_g)
                 rows[sl] = np.concatenate(rp)
                 cols[sl] = np.concatenate(cp)
+                count += len(sl)
+            for make in thunks:
+                r, c, sl = make()
+                rows[sl] = r
+                cols[sl] = c
+                count += len(sl)
+            assert count == self.nnz_g, (count, self.nnz_g)
             self._G_rows, self._G_cols = rows, cols
             self._g_parts = None
         return self._G_rows, self._G_cols
