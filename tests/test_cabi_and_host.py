@@ -276,3 +276,20 @@ def test_compiled_host_evaluates_without_python(name, tmp_path):
     assert np.all(hr >= hc)                                           # lower triangle
     assert np.array_equal(jv, ref["jac"][0][pj])
     assert np.array_equal(hv, ref["hess"][0][ph])
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: ``include/pcx.h`` compiles as C99 with -pedantic (no C++
+    types, no torch types in the signatures) and a C program links against the library."""
+    import subprocess
+    src = tmp_path / "c99.c"
+    src.write_text('#include "pcx.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%s %d\\n", pcx_version(), pcx_table_count()); return 0; }\n')
+    libdir = os.path.join(ROOT, "pycollo_b200")
+    exe = tmp_path / "c99"
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror",
+                          f"-I{os.path.join(ROOT, 'include')}", str(src), f"-L{libdir}", "-lpcx",
+                          f"-Wl,-rpath,{libdir}", "-o", str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("pcx ")
