@@ -55,7 +55,7 @@ def lower_problem(ocp, meshes=None, share_bodies=None, **structure_kwargs):
         quad = Quadrature(ocp.settings.quadrature_method)
         meshes = [PhaseMeshData(quad, ph.mesh, 2, 20) for ph in ocp.phases]
     S = NLPStructure(ir, pds, ptd, meshes,
-                     prune=ocp.settings.prune_zero_quadrature_coefficients,
+                     prune=getattr(ocp.settings, "prune_zero_quadrature_coefficients", True),
                      **structure_kwargs)
     header, layouts = codegen.generate(ir, pds, ptd, S, share=share_bodies)
     return SimpleNamespace(ir=ir, pds=pds, ptd=ptd, S=S, header=header,
