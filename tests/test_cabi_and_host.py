@@ -293,3 +293,46 @@ def test_header_is_plain_c99(tmp_path):
     assert res.returncode == 0, res.stderr[-2000:]
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("pcx ")
+
+
+def test_spec_reader_survives_corrupted_files(tmp_path):
+    """200 random corruptions of a valid spec file (flipped bytes, truncations, absurd length
+    fields): ``pcx_create_from_file`` answers PCX_EINVAL -- or gets as far as the device --
+    and never crashes.  Run in a subprocess so that a crash would fail this test only."""
+    import subprocess
+    import sys
+    from helpers import build_case
+    low, _, scal = build_case(examples.brachistochrone(), "lobatto", 10, 4, oracle=False)
+    good = str(tmp_path / "good.pcxspec")
+    E.Engine.write_spec(good, low.S, low.layouts, low.header, scal)
+    script = tmp_path / "fuzz.py"
+    script.write_text(f"""
+import ctypes, random, sys
+sys.path.insert(0, {ROOT!r})
+from pycollo_b200 import engine as E
+data = open({good!r}, 'rb').read()
+lib = E.load_library(); h = ctypes.c_void_p()
+random.seed(7)
+for it in range(200):
+    b = bytearray(data)
+    mode = it % 4
+    if mode == 0:
+        for _ in range(random.randint(1, 8)):
+            b[random.randrange(len(b))] = random.randrange(256)
+    elif mode == 1:
+        n = random.randrange(0, len(b)); b = b[:n - n % 8]
+    elif mode == 2:
+        off = random.randrange(0, len(b) // 8) * 8
+        b[off:off + 8] = random.choice([b'\\xff' * 8, (2 ** 40).to_bytes(8, 'little'), bytes(8),
+                                        len(b).to_bytes(8, 'little'), (2 ** 63 - 1).to_bytes(8, 'little')])
+    else:
+        b[random.randrange(8, 200)] = random.randrange(256)
+    open({str(tmp_path / 'bad.pcxspec')!r}, 'wb').write(bytes(b))
+    rc = lib.pcx_create_from_file({str(tmp_path / 'bad.pcxspec')!r}.encode(), 0, ctypes.byref(h))
+    if rc == 0:
+        lib.pcx_destroy(h); h = ctypes.c_void_p()
+    assert rc in (0, -1, -2, -3, -4), rc
+print('survived')
+""")
+    res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "survived" in res.stdout, (res.returncode, res.stderr[-1500:])
