@@ -144,3 +144,50 @@ def test_restatements_agree_on_cart_pole_small(method):
         Ek = ExpandedNLP(ocp, ir.full_bounds, meshes, prune=False)
         assert (len(Bk.G_structure()[0]), len(Bk.H_structure()[0])) == (236, 35)
         assert (len(Ek.G_rows), len(Ek.H_rows)) == (236, 35)
+
+
+def test_lowered_equations_match_the_reference_known_answers():
+    """The reference's own known-answer tests for the substituted problem functions
+    (``tests/unit/test_backend_casadi.py:1328-1402`` double pendulum -- phase-level
+    auxiliary data shadow problem-level ones: g = -9.81, k1 = 1/12 -- ``:1405-1435``
+    brachistochrone, ``:1470-1490`` integrand, ``:1521-1566`` objectives) restated in the
+    user basis and compared at random points with what the lowering hands the code
+    generator (``symbolic.build_ir``)."""
+    import sympy as sym
+    from examples import problems
+    from pycollo_b200.symbolic import build_ir
+    rng = np.random.default_rng(12)
+
+    def same(ours, expect, syms, n=6):
+        f = sym.lambdify(syms, [sym.sympify(e) for e in ours], "numpy")
+        g = sym.lambdify(syms, [sym.sympify(e) for e in expect], "numpy")
+        for _ in range(n):
+            pt = rng.uniform(0.3, 1.4, len(syms))
+            np.testing.assert_allclose(np.array(f(*pt), dtype=float), np.array(g(*pt), dtype=float),
+                                       rtol=1e-13, atol=1e-13)
+
+    ir = build_ir(problems.double_pendulum())
+    ph = ir.phases[0]
+    a0, a1, v0, v1 = ph.y
+    T0, T1 = ph.u
+    m0, p0 = ir.s
+    g_, d0, k0, m1, p1, k1 = -9.81, 0.5, sym.Rational(1, 12), 1.0, 0.5, sym.Rational(1, 12)
+    l0 = p0 + d0
+    I0, I1 = m0 * (k0 ** 2 + p0 ** 2), m1 * (k1 ** 2 + p1 ** 2)
+    c0, s0, c1, s1 = sym.cos(a0), sym.sin(a0), sym.cos(a1), sym.sin(a1)
+    M00, M01, M11 = I0 + m1 * l0 ** 2, m1 * p1 * l0 * (s0 * s1 + c0 * c1), I1
+    M10 = M01
+    K0 = T0 + g_ * (m0 * p0 + m1 * l0) * c0 + m1 * p1 * l0 * (s1 * c0 - s0 * c1) * v1 ** 2
+    K1 = T1 + g_ * m1 * p1 * c1 + m1 * p1 * l0 * (s0 * c1 - s1 * c0) * v0 ** 2
+    detM = M00 * M11 - M01 * M10
+    expect = (v0, v1, (M11 * K0 - M01 * K1) / detM, (M00 * K1 - M10 * K0) / detM)
+    assert len(ph.f) == 4 and len(ph.p) == 0 and len(ph.g) == 1
+    same(ph.f, expect, [a0, a1, v0, v1, T0, T1, m0, p0])
+    same(ph.g, (T0 ** 2 + T1 ** 2,), [T0, T1])
+    assert str(ir.J) == "q0_P0"                                   # J = the integral variable
+
+    ir = build_ir(problems.brachistochrone())
+    ph = ir.phases[0]
+    (x, y, v), (u,) = ph.y, ph.u
+    same(ph.f, (v * sym.sin(u), v * sym.cos(u), 9.81 * sym.cos(u)), [x, y, v, u])
+    assert str(ir.J) == "tF_P0"                                   # J = the final time
