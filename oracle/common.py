@@ -10,10 +10,12 @@ arithmetic lives in CasADi's SX VM, not under ``/root/reference``.  These files
 restate the *published algebra* of that path and are pinned against every
 known answer the reference's tests hold for it (``tests/test_oracle_pins.py``):
 J, g, c, V, r, x<->x_tilde of ``tests/unit/test_iteration.py:290-385`` and
-``tests/unit/test_iteration_scaling.py``.  **G and H have no reference pins
-anywhere: for those, parity is "unpinned" against CasADi and
-is established against this oracle, whose two restatements check each other
-and are checked against central differences.**
+``tests/unit/test_iteration_scaling.py``.  G and H (no known answers anywhere in the
+reference's tests) are pinned against golden vectors produced by
+EXECUTING the unmodified reference package under the stand-ins of ``oracle/refshim``
+(``oracle/make_golden_nlp.py`` -> ``tests/golden/nlp_*.npz``,
+``tests/test_reference_goldens.py``); the two restatements also check each other and are
+checked against central differences.
 
 What this module restates
 -------------------------
