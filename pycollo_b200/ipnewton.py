@@ -17,14 +17,14 @@ import scipy.sparse as sp
 
 def solve(cb, x0, x_lo, x_hi, c_lo, c_hi, tol=1e-8, max_iter=500, verbose=False):
     """Primal-dual interior-point Newton method in the style of IPOPT's basic
-    algorithm (Waechter & Biegler 2006, sections 2-3, without the filter and the
-    restoration phase): slacks for inequality rows, log barrier for the variable
-    bounds, exact Hessian of the Lagrangian, fraction-to-the-boundary rule, l1
-    merit line search, diagonal regularisation when the reduced Hessian is not
-    positive definite, monotone barrier update.  Deterministic: the sequence of
+    algorithm (Waechter & Biegler 2006, sections 2-3, with its filter acceptance test
+    but without the restoration phase): slacks for inequality rows, log barrier for
+    the variable bounds, exact Hessian of the Lagrangian, fraction-to-the-boundary
+    rule, backtracking line search, diagonal regularisation when the reduced Hessian
+    is not positive definite, monotone barrier update.  Deterministic: the sequence of
     iterates is a function of the callback values only.
 
-    Returns ``SimpleNamespace(x, fun, nit, constr_violation, kkt_error, success)``.
+    Returns ``SimpleNamespace(x, fun, nit, constr_violation, kkt_error, success, lam)``.
     """
     from types import SimpleNamespace
     import scipy.sparse.linalg as spla
