@@ -459,6 +459,41 @@ class Engine:
             fh.write(b"".join(out))
         return path
 
+    @staticmethod
+    def read_spec(path):
+        """Parse a spec file back (the layout ``include/pcx.h`` documents): dict with the
+        scalar ``fields``, the ``header`` text, ``tables`` (name -> raw bytes) and the four
+        ``scaling`` arrays.  For inspection and for pinning the format in the tests; the
+        reader that matters is ``pcx_create_from_file``."""
+        raw = open(path, "rb").read()
+        if raw[:8] != b"PCXSPEC1" or len(raw) % 8:
+            raise PcxError("not a PCXSPEC1 file")
+        pos = 8
+
+        def take(n):
+            nonlocal pos
+            out = raw[pos:pos + n]
+            if len(out) != n:
+                raise PcxError("truncated spec file")
+            pos += n + (-n % 8)
+            return out
+        i32 = np.frombuffer(take(40), dtype="<i4")
+        i64 = np.frombuffer(take(48), dtype="<i8")
+        names = ("threads", "batch", "num_tiles", "nvmax", "n_border", "bv_size", "nred_max",
+                 "btab_len", "reserved", "num_tables", "num_x", "num_c", "num_dy", "nnz_g",
+                 "nnz_h", "smem_bytes")
+        fields = dict(zip(names, [int(v) for v in i32] + [int(v) for v in i64]))
+        header = take(int(np.frombuffer(take(8), dtype="<i8")[0]))[:-1].decode()
+        tables = {}
+        for _ in range(fields["num_tables"]):
+            name = take(int(np.frombuffer(take(8), dtype="<i8")[0]))[:-1].decode()
+            tables[name] = take(int(np.frombuffer(take(8), dtype="<i8")[0]))
+        ns = np.frombuffer(take(32), dtype="<i8")
+        scaling = [np.frombuffer(take(8 * int(n)), dtype="<f8") for n in ns]
+        if pos != len(raw):
+            raise PcxError("trailing bytes in spec file")
+        return dict(fields=fields, header=header, tables=tables, scaling=scaling)
+
     # -- host-space convenience (numpy in / numpy out) ---------------------
     def eval_host(self, what, x, lam=None, sigma=None):
         S, B = self.S, self.batch

@@ -194,6 +194,17 @@ def test_spec_file_is_parsed_and_bad_files_are_rejected(tmp_path):
     low, _, scal = build_case(examples.brachistochrone(), "lobatto", 10, 4, oracle=False)
     path = str(tmp_path / "br.pcxspec")
     E.Engine.write_spec(path, low.S, low.layouts, low.header, scal)
+    # the documented layout, read back in Python: nothing lost, nothing reordered
+    back = E.Engine.read_spec(path)
+    tables = E.build_tables(low.S, low.layouts)
+    assert back["header"] == low.header
+    assert back["fields"]["num_x"] == low.S.num_x and back["fields"]["nnz_g"] == low.S.nnz_g
+    assert back["fields"]["num_tiles"] == low.S.num_tiles and back["fields"]["threads"] == low.S.threads
+    for name, arr in tables.items():
+        assert back["tables"][name] == arr.tobytes(), name
+    assert back["tables"]["g_rows"] == low.S.G_structure()[0].astype(np.int64).tobytes()
+    for got, want in zip(back["scaling"], E.scaling_tables(low.S, low.layouts, *scal)):
+        assert np.array_equal(got, want)
     lib = E.load_library()
     h = ctypes.c_void_p()
     rc = lib.pcx_create_from_file(path.encode(), 0, ctypes.byref(h))
